@@ -1,0 +1,175 @@
+/* saunet_b200.h -- C ABI of libsaunet_b200.so (sm_100a).
+ *
+ * The reference (sunjesse/shape-attentive-unet) is pure Python/PyTorch and has
+ * NO FFI/plugin layer for this path: its hot path calls
+ * stock torch ops.  Each entry point below therefore names the reference
+ * call site(s) whose ATen op it replaces (paths relative to /root/reference).
+ * A reference maintainer binds these with ctypes.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, negative = SAUNET_ERR_*;
+ *     saunet_last_error() gives the thread-local message; nothing throws/aborts.
+ *   - all pointers are DEVICE pointers unless the name says host; the library
+ *     never allocates, frees or retains caller memory; scratch is caller-owned.
+ *   - activations are fp32 NHWC ("channels_last"): element (b,y,x,c) lives at
+ *     ptr[((b*H + y)*W + x)*ld + c]; `ld` >= C lets a call address a channel
+ *     slice of a wider (concatenated) buffer without a copy.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it.
+ *   - no CPU fallback exists anywhere in this library.
+ */
+#ifndef SAUNET_B200_H
+#define SAUNET_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAUNET_OK 0
+#define SAUNET_ERR_BAD_SHAPE (-1)
+#define SAUNET_ERR_BAD_DTYPE (-2)
+#define SAUNET_ERR_BAD_ALIGN (-3)
+#define SAUNET_ERR_WORKSPACE (-4)
+#define SAUNET_ERR_CUDA (-5)
+
+#define SAUNET_ACT_NONE 0
+#define SAUNET_ACT_RELU 1
+#define SAUNET_ACT_SIGMOID 2
+
+int saunet_version(void);
+const char* saunet_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+long long saunet_launch_count(void);
+
+/* ---- implicit-GEMM convolution --------------------------------------------------------------
+ * One descriptor drives forward, data-gradient and (with saunet_conv2d_wgrad) weight-gradient of
+ * every conv-like op on the path:
+ *   nn.Conv2d 1x1/3x3/7x7  (torchvision densenet.py:31-133,170; models/models.py:118-123,280-301,324;
+ *                           models/resnet.py:24-27; models/attention_blocks.py:31-36,149-150,215-218)
+ *   nn.ConvTranspose2d k4 s2 p1 (models/attention_blocks.py:179-183; models/models.py:211) as 4 phases
+ *   F.conv2d in GatedSpatialConv2d (models/GSConv.py:56-57)
+ * GEMM view: rows = output-grid pixels (b,i,j), i<Hg, j<Wg; K = KH*KW*Cin ordered (ky,kx,c); N = Cout.
+ *   input pixel for tap (ky,kx) : (i*sy + ky + offy, j*sx + kx + offx), zero outside the image
+ *   output pixel                : (i*osy + oy0,     j*osx + ox0)
+ * Optional fused prologue on the gathered input (the pre-activation BatchNorm+ReLU of DenseNet,
+ * densenet.py:47-50): a = relu?(x*in_scale[c] + in_shift[c]), applied BEFORE zero padding.
+ * Optional fused epilogue: + bias[n]; per-output-channel sum / sum-of-squares accumulated (double
+ * atomics) into stat_sum/stat_sumsq for the BatchNorm that follows; * (row_scale[p] + row_scale_add)
+ * (the GSConv gate, GSConv.py:55); activation; accumulate into y.
+ */
+typedef struct saunet_conv_desc {
+    const float* x; int x_ld; int B, Hin, Win, Cin;
+    const float* w;              /* packed [KH*KW*Cin][Cout] (see saunet_pack_weights) */
+    int Cout, KH, KW;
+    int Hg, Wg, sy, sx, offy, offx;
+    float* y; int y_ld; int Hout, Wout, osy, osx, oy0, ox0;
+    const float* in_scale; const float* in_shift; int in_relu;
+    const float* bias;
+    const float* row_scale; float row_scale_add;
+    int act;                     /* SAUNET_ACT_* */
+    int accumulate;              /* y += result instead of y = result */
+    double* stat_sum; double* stat_sumsq;
+} saunet_conv_desc;
+
+int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream);
+
+/* weight gradient: dw[(ky,kx,cb)][ca] += sum_pixels P[pix][ca] * Q[gather(pix,ky,kx)][cb]
+ * (regular conv: P = dY, Q = x; conv-transpose: P = x, Q = dY gathered with stride 2).
+ * Q may carry the same prologue as the forward (recomputes relu(bn(x)) instead of storing it).
+ * dw must be zeroed by the caller (accumulated with fp32 atomics over pixel splits). */
+typedef struct saunet_wgrad_desc {
+    const float* p; int p_ld; int Ca;
+    const float* q; int q_ld; int Cb; int B, Hq, Wq;
+    int KH, KW, Hg, Wg, sy, sx, offy, offx;
+    const float* q_scale; const float* q_shift; int q_relu;
+    float* dw;                   /* packed [KH*KW*Cb][Ca] */
+} saunet_wgrad_desc;
+int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream);
+
+/* weight (un)packing between PyTorch parameter layout w[A][Bc][KH][KW] and the packed GEMM layouts.
+ *  mode 0: packed[(t,b)][a]       = w[a][b][t]                      (conv fwd, convT dgrad)
+ *  mode 1: packed[(t,a)][b]       = w[a][b][KH*KW-1-t]              (stride-1 conv dgrad)
+ *  mode 2: packed[ph][(ty,tx,a)][b] = w[a][b][3-pa-2ty][3-pb-2tx], ph = pa*2+pb  (convT 4x4 s2 p1 fwd phases)
+ * unpack: w_grad[a][b][t] (+)= packed[(t,b)][a]  (mode 0 only). */
+int saunet_pack_weights(const float* w, float* packed, int A, int Bc, int KH, int KW, int mode, void* stream);
+int saunet_unpack_wgrad(const float* packed, float* wgrad, int A, int Bc, int KH, int KW, int accumulate, void* stream);
+
+/* ---- batch norm (nn.BatchNorm2d / SynchronizedBatchNorm2d outside DataParallel == F.batch_norm;
+ *      lib/nn/modules/batchnorm.py:58-61; Appendix A of SURVEY.md) ---------------------------------- */
+/* per-channel sum and sum of squares over npix pixels, accumulated into double[C] each (caller zeroes;
+ * sum and sumsq must belong to one allocation with sumsq >= sum + C) */
+int saunet_channel_stats(const float* x, int ld, int C, long long npix, double* sum, double* sumsq, void* stream);
+/* dst[i] += (float)src[i]  -- folds an fp64 reduction (e.g. a conv bias gradient = column sums) into an fp32 grad */
+int saunet_add_d2f(const double* src, float* dst, int n, void* stream);
+/* state = float[4][C]: scale, shift, mean, invstd.  training: batch stats from sum/sumsq/count and
+ * running-stat update (momentum; unbiased var);  eval: from running stats. */
+int saunet_bn_finalize(const double* sum, const double* sumsq, double count, const float* gamma, const float* beta,
+                       float* running_mean, float* running_var, float momentum, float eps, int training, int C,
+                       float* state, void* stream);
+/* y = act(x*scale[c] + shift[c] (+ residual)) */
+int saunet_affine_act(const float* x, int x_ld, const float* scale, const float* shift, const float* residual,
+                      int r_ld, float* y, int y_ld, int C, long long npix, int act, void* stream);
+/* g = dy * act'(.)  where the ReLU mask comes from `out` (post-activation tensor) if given, else from
+ * recomputing x*scale+shift > 0;  red[0][c] += sum g, red[1][c] += sum g*xhat  (double[2][C], caller zeroes) */
+int saunet_bn_bwd_reduce(const float* dy, int dy_ld, const float* x, int x_ld, const float* out, int out_ld,
+                         const float* state, int C, long long npix, int act, double* red, void* stream);
+/* dx (+)= gamma*invstd*(g - sum_g/n - xhat*sum_gx/n)  [training]  or  g*scale [eval];
+ * dres (+)= g if dres != NULL;  dgamma[c] += sum_gx, dbeta[c] += sum_g (fp32 parameter grads) */
+int saunet_bn_bwd_apply(const float* dy, int dy_ld, const float* x, int x_ld, const float* out, int out_ld,
+                        const float* state, const float* gamma, const double* red, int C, long long npix, int act,
+                        int training, float* dx, int dx_ld, int dx_acc, float* dres, int dres_ld, int dres_acc,
+                        float* dgamma, float* dbeta, void* stream);
+
+/* ---- pointwise / resampling ------------------------------------------------------------------- */
+/* F.interpolate(mode='bilinear', align_corners=True) models/models.py:337-389 */
+int saunet_bilinear_fwd(const float* x, int x_ld, int B, int Hin, int Win, int C, float* y, int y_ld, int Hout,
+                        int Wout, void* stream);
+int saunet_bilinear_bwd(const float* dy, int dy_ld, int B, int Hin, int Win, int C, float* dx, int dx_ld, int Hout,
+                        int Wout, int accumulate, void* stream);
+/* nn.AvgPool2d(2,2) densenet.py:133 ; nn.MaxPool2d(2,2) models/models.py:269,376 */
+int saunet_avgpool2_fwd(const float* x, int x_ld, int B, int Hin, int Win, int C, float* y, int y_ld, void* stream);
+int saunet_avgpool2_bwd(const float* dy, int dy_ld, int B, int Hin, int Win, int C, float* dx, int dx_ld, int accumulate, void* stream);
+int saunet_maxpool2_fwd(const float* x, int x_ld, int B, int Hin, int Win, int C, float* y, int y_ld, void* stream);
+int saunet_maxpool2_bwd(const float* dy, int dy_ld, const float* x, int x_ld, int B, int Hin, int Win, int C, float* dx,
+                        int dx_ld, int accumulate, void* stream);
+/* nn.AdaptiveAvgPool2d(1) models/attention_blocks.py:32,51 : y[b][c] = mean over HW */
+int saunet_gap_fwd(const float* x, int x_ld, int B, long long HW, int C, float* y, void* stream);
+int saunet_gap_bwd(const float* dy, int B, long long HW, int C, float* dx, int dx_ld, int accumulate, void* stream);
+/* dz = dy * act'(y) from the activation OUTPUT y */
+int saunet_act_bwd(const float* dy, int dy_ld, const float* y, int y_ld, float* dz, int dz_ld, int C, long long npix, int act, void* stream);
+/* DualAttBlock combine (attention_blocks.py:57,237): out = fused * (1 + S[p]) * cvec[b][c] */
+int saunet_dualatt_combine_fwd(const float* fused, int f_ld, const float* S, const float* cvec, int B, long long HW,
+                               int C, float* out, int o_ld, void* stream);
+/* dfused (+)= dout*(1+S)*c ; dS[p] (=) sum_c dout*fused*c ; dcvec[b][c] += sum_p dout*fused*(1+S) (caller zeroes dcvec) */
+int saunet_dualatt_combine_bwd(const float* dout, int do_ld, const float* fused, int f_ld, const float* S,
+                               const float* cvec, int B, long long HW, int C, float* dfused, int df_ld, int df_acc,
+                               float* dS, float* dcvec, void* stream);
+/* GSConv gate backward (GSConv.py:55-57 with out = (alpha+1)*conv(x)):
+ * du = dout*(alpha+1) ; dalpha[p] (+)= sum_c dout*out/(alpha+1) */
+int saunet_rowscale_bwd(const float* dout, int do_ld, const float* out, int o_ld, const float* alpha, int C,
+                        long long npix, float* du, int du_ld, float* dalpha, int da_acc, void* stream);
+/* strided channel-slice copy / accumulate: dst[p][0:C] (+)= src[p][0:C] */
+int saunet_copy_slice(const float* src, int s_ld, float* dst, int d_ld, int C, long long npix, int accumulate, void* stream);
+/* layout conversion at the module boundary (NCHW <-> NHWC) */
+int saunet_nchw_to_nhwc(const float* src, float* dst, int dst_ld, int B, int C, long long HW, void* stream);
+int saunet_nhwc_to_nchw(const float* src, int src_ld, float* dst, int B, int C, long long HW, void* stream);
+
+/* ---- loss: loss.py:51-88 (dice_loss), :149-159 (DualLoss.forward) --------------------------------
+ * logits NHWC [npix][C] (C <= 8), edge prob [npix], seg target int64 [npix], edge target float [npix].
+ * acc = double[2 + 2*C + 1]: [0]=sum w*nll, [1]=sum w, [2..2+C)=I_c, [2+C..2+2C)=Card_c, [2+2C]=sum bce (caller zeroes)
+ * finalize writes loss[0]=total, [1]=dice, [2]=ce, [3]=bce (float). */
+int saunet_dual_loss_fwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
+                         long long npix, int C, const float* class_w, double* acc, float* loss, void* stream);
+int saunet_dual_loss_bwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
+                         long long npix, int C, const float* class_w, const double* acc, const float* dloss,
+                         float* dlogits, int dl_ld, float* dedge, void* stream);
+
+/* ---- Canny fusion: models/models.py:358-364 (np.mean(axis=1).astype(uint8) + cv2.Canny(im,10,100)) ----
+ * x is the fp32 image, NCHW [B][C][H][W]; out is float [B][H][W] in {0,255}.
+ * workspace: saunet_canny_workspace_bytes(B,H,W) bytes. */
+long long saunet_canny_workspace_bytes(int B, int H, int W);
+int saunet_canny_fwd(const float* x_nchw, int B, int C, int H, int W, int low, int high, float* out, void* workspace,
+                     long long workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

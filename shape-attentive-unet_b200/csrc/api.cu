@@ -1,0 +1,44 @@
+// api.cu -- library-wide state (error string, launch counter, version) and conv dispatch.
+#include "common.cuh"
+#include <atomic>
+#include <string.h>
+
+namespace saunet {
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int conv_fwd_simt(const saunet_conv_desc* d, cudaStream_t st);
+int conv_wgrad_simt(const saunet_wgrad_desc* d, cudaStream_t st);
+}  // namespace saunet
+
+using namespace saunet;
+
+extern "C" int saunet_version(void) { return 100; }
+extern "C" const char* saunet_last_error(void) { return g_err; }
+extern "C" long long saunet_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
+    SAUNET_CHECK_ARG(d && d->x && d->w && d->y, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: null pointer");
+    SAUNET_CHECK_ARG(d->B > 0 && d->Hin > 0 && d->Win > 0 && d->Cin > 0 && d->Cout > 0 && d->KH > 0 && d->KW > 0 &&
+                     d->Hg > 0 && d->Wg > 0 && d->sy > 0 && d->sx > 0 && d->osy > 0 && d->osx > 0,
+                     SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: non-positive dimension");
+    SAUNET_CHECK_ARG(d->x_ld >= d->Cin && d->y_ld >= d->Cout, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: ld smaller than channel count");
+    SAUNET_CHECK_ARG((d->Hg - 1) * d->osy + d->oy0 < d->Hout && (d->Wg - 1) * d->osx + d->ox0 < d->Wout && d->oy0 >= 0 && d->ox0 >= 0,
+                     SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: output grid exceeds output tensor");
+    SAUNET_CHECK_ARG((d->in_scale == nullptr) == (d->in_shift == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: in_scale/in_shift mismatch");
+    SAUNET_CHECK_ARG((d->stat_sum == nullptr) == (d->stat_sumsq == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: stat_sum/stat_sumsq mismatch");
+    SAUNET_CHECK_ARG(d->act >= 0 && d->act <= 2, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: bad activation %d", d->act);
+    return conv_fwd_simt(d, (cudaStream_t)stream);
+}
+
+extern "C" int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream) {
+    SAUNET_CHECK_ARG(d && d->p && d->q && d->dw, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: null pointer");
+    SAUNET_CHECK_ARG(d->B > 0 && d->Hq > 0 && d->Wq > 0 && d->Ca > 0 && d->Cb > 0 && d->KH > 0 && d->KW > 0 && d->Hg > 0 &&
+                     d->Wg > 0 && d->sy > 0 && d->sx > 0, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: non-positive dimension");
+    SAUNET_CHECK_ARG(d->p_ld >= d->Ca && d->q_ld >= d->Cb, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: ld smaller than channel count");
+    SAUNET_CHECK_ARG((d->q_scale == nullptr) == (d->q_shift == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: q_scale/q_shift mismatch");
+    return conv_wgrad_simt(d, (cudaStream_t)stream);
+}

@@ -1,0 +1,301 @@
+// norm.cu -- BatchNorm family on NHWC fp32: per-channel statistics, finalize (+running stats),
+// affine+activation apply, and the two-pass backward (reduce, apply).  All HBM-bound: coalesced
+// 128-bit loads along the channel axis, fp64 accumulation of the per-channel sums.
+#include "common.cuh"
+
+namespace saunet {
+
+// ---- generic per-channel reduction over pixels ------------------------------------------------
+// Thread (r, l): l indexes a VEC-wide channel group, r a pixel row inside the block.  Each op adds
+// NV quantities per channel.  Result accumulated with double atomics into out[NV][C].
+template <int VEC, typename Op>
+__global__ void __launch_bounds__(256) chan_reduce_kernel(Op op, int C, long long npix, double* __restrict__ out, long long vstride) {
+    constexpr int NV = Op::NV;
+    __shared__ double red[NV * VEC * 256];
+    const int L = C / VEC;                       // channel groups per pixel
+    const int lanes = L < 256 ? L : 256;
+    const int rows = 256 / lanes;
+    const int tid = threadIdx.x;
+    const int l = tid % lanes, r = tid / lanes;
+    const bool active = r < rows;
+    for (int l0 = 0; l0 < L; l0 += lanes) {
+        const int lg = l0 + l;
+        double acc[NV][VEC];
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[v][e] = 0.0;
+        if (active && lg < L) {
+            for (long long p = (long long)blockIdx.x * rows + r; p < npix; p += (long long)gridDim.x * rows)
+                op(p, lg * VEC, acc);
+        }
+        if (rows > 1) {
+            __syncthreads();
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) red[(v * VEC + e) * 256 + tid] = acc[v][e];
+            __syncthreads();
+            if (r == 0 && lg < L) {
+                for (int rr = 1; rr < rows; ++rr)
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) acc[v][e] += red[(v * VEC + e) * 256 + rr * lanes + l];
+            }
+        }
+        if (r == 0 && lg < L) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) atomicAdd(out + (size_t)v * vstride + lg * VEC + e, acc[v][e]);
+        }
+    }
+}
+
+template <int VEC> struct Vec;
+template <> struct Vec<1> {
+    float v[1];
+    __device__ static Vec load(const float* p) { Vec r; r.v[0] = __ldg(p); return r; }
+    __device__ void store(float* p) const { p[0] = v[0]; }
+};
+template <> struct Vec<4> {
+    float v[4];
+    __device__ static Vec load(const float* p) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p)); Vec r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r;
+    }
+    __device__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+template <int VEC>
+struct StatsOp {
+    static constexpr int NV = 2;
+    const float* x; int ld;
+    __device__ void operator()(long long p, int c, double (&acc)[2][VEC]) const {
+        Vec<VEC> v = Vec<VEC>::load(x + (size_t)p * ld + c);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) { double t = v.v[e]; acc[0][e] += t; acc[1][e] += t * t; }
+    }
+};
+
+template <int VEC>
+struct BnBwdOp {
+    static constexpr int NV = 2;
+    const float* dy; int dy_ld; const float* x; int x_ld; const float* out; int out_ld;
+    const float* state; int C; int act;
+    __device__ void operator()(long long p, int c, double (&acc)[2][VEC]) const {
+        Vec<VEC> g = Vec<VEC>::load(dy + (size_t)p * dy_ld + c);
+        Vec<VEC> xv = Vec<VEC>::load(x + (size_t)p * x_ld + c);
+        Vec<VEC> ov;
+        if (act == SAUNET_ACT_RELU && out) ov = Vec<VEC>::load(out + (size_t)p * out_ld + c);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const float mean = state[2 * C + c + e], invstd = state[3 * C + c + e];
+            float gg = g.v[e];
+            if (act == SAUNET_ACT_RELU) {
+                float z = out ? ov.v[e] : fmaf(xv.v[e], state[c + e], state[C + c + e]);
+                if (!(z > 0.f)) gg = 0.f;
+            }
+            float xh = (xv.v[e] - mean) * invstd;
+            acc[0][e] += (double)gg; acc[1][e] += (double)gg * (double)xh;
+        }
+    }
+};
+
+template <typename Op1, typename Op4>
+static int launch_reduce(const Op1& o1, const Op4& o4, bool vec, int C, long long npix, double* out, long long vstride, cudaStream_t st, const char* name) {
+    int L = vec ? C / 4 : C;
+    int lanes = L < 256 ? L : 256;
+    int rows = 256 / lanes;
+    long long want = (npix + rows - 1) / rows;
+    // keep >= 8 pixels per thread when possible, cap at 8 CTAs/SM
+    long long cap = (long long)kNumSMs * 8;
+    long long blocks = want / 8; if (blocks < 1) blocks = 1; if (blocks > cap) blocks = cap;
+    if (vec) chan_reduce_kernel<4, Op4><<<(int)blocks, 256, 0, st>>>(o4, C, npix, out, vstride);
+    else chan_reduce_kernel<1, Op1><<<(int)blocks, 256, 0, st>>>(o1, C, npix, out, vstride);
+    SAUNET_CHECK_LAUNCH(name);
+    return SAUNET_OK;
+}
+
+// ---- finalize -----------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float* running_mean,
+                                   float* running_var, float momentum, float eps, int training, int C, float* __restrict__ state) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mean, var;
+    if (training) {
+        mean = sum[c] / count;
+        var = sumsq[c] / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        if (running_mean) {
+            double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+            running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+            running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unbiased);
+        }
+    } else {
+        mean = running_mean[c]; var = running_var[c];
+    }
+    float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+    float scale = g * invstd;
+    state[c] = scale;
+    state[C + c] = b - (float)mean * scale;
+    state[2 * C + c] = (float)mean;
+    state[3 * C + c] = invstd;
+}
+
+// ---- apply ---------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, const float* __restrict__ res, int r_ld,
+                                                         float* __restrict__ y, int y_ld, int C, long long npix, int act) {
+    const int L = C / VEC;
+    const long long n = npix * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        long long p = idx / L; int c = (int)(idx - p * L) * VEC;
+        Vec<VEC> v = Vec<VEC>::load(x + (size_t)p * x_ld + c);
+        Vec<VEC> rv;
+        if (res) rv = Vec<VEC>::load(res + (size_t)p * r_ld + c);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            float t = scale ? fmaf(v.v[e], scale[c + e], shift[c + e]) : v.v[e];
+            if (res) t += rv.v[e];
+            v.v[e] = apply_act(t, act);
+        }
+        v.store(y + (size_t)p * y_ld + c);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ x, int x_ld,
+                                                           const float* __restrict__ out, int out_ld, const float* __restrict__ state,
+                                                           const float* __restrict__ gamma, const double* __restrict__ red, int C,
+                                                           long long npix, int act, int training, float* dx, int dx_ld, int dx_acc,
+                                                           float* dres, int dres_ld, int dres_acc, float* dgamma, float* dbeta) {
+    const int L = C / VEC;
+    const long long n = npix * L;
+    const double inv_n = 1.0 / (double)npix;
+    if (blockIdx.x == 0 && dgamma) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { dbeta[c] += (float)red[c]; dgamma[c] += (float)red[C + c]; }
+    }
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        long long p = idx / L; int c = (int)(idx - p * L) * VEC;
+        Vec<VEC> g = Vec<VEC>::load(dy + (size_t)p * dy_ld + c);
+        Vec<VEC> xv = Vec<VEC>::load(x + (size_t)p * x_ld + c);
+        Vec<VEC> ov;
+        if (act == SAUNET_ACT_RELU && out) ov = Vec<VEC>::load(out + (size_t)p * out_ld + c);
+        Vec<VEC> dxv, drv;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int cc = c + e;
+            float gg = g.v[e];
+            if (act == SAUNET_ACT_RELU) {
+                float z = out ? ov.v[e] : fmaf(xv.v[e], state[cc], state[C + cc]);
+                if (!(z > 0.f)) gg = 0.f;
+            }
+            drv.v[e] = gg;
+            const float invstd = state[3 * C + cc];
+            const float gs = (gamma ? gamma[cc] : 1.f) * invstd;
+            if (training) {
+                float xh = (xv.v[e] - state[2 * C + cc]) * invstd;
+                float m1 = (float)(red[cc] * inv_n), m2 = (float)(red[C + cc] * inv_n);
+                dxv.v[e] = gs * (gg - m1 - xh * m2);
+            } else {
+                dxv.v[e] = gs * gg;
+            }
+        }
+        if (dx) {
+            float* dp = dx + (size_t)p * dx_ld + c;
+            if (dx_acc) { Vec<VEC> o = Vec<VEC>::load(dp);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) dxv.v[e] += o.v[e]; }
+            dxv.store(dp);
+        }
+        if (dres) {
+            float* dp = dres + (size_t)p * dres_ld + c;
+            if (dres_acc) { Vec<VEC> o = Vec<VEC>::load(dp);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) drv.v[e] += o.v[e]; }
+            drv.store(dp);
+        }
+    }
+}
+
+static inline int ew_blocks(long long n) {
+    long long b = (n + 255) / 256; long long cap = (long long)kNumSMs * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+static inline bool vec_ok(int C, std::initializer_list<std::pair<const void*, int>> ts) {
+    if (C % 4) return false;
+    for (auto& t : ts) if (t.first && (!aligned16(t.first) || (t.second % 4))) return false;
+    return true;
+}
+
+}  // namespace saunet
+
+using namespace saunet;
+
+extern "C" int saunet_channel_stats(const float* x, int ld, int C, long long npix, double* sum, double* sumsq, void* stream) {
+    SAUNET_CHECK_ARG(x && sum && sumsq && C > 0 && npix > 0 && ld >= C, SAUNET_ERR_BAD_SHAPE, "channel_stats: bad args");
+    SAUNET_CHECK_ARG(sumsq >= sum + C, SAUNET_ERR_BAD_SHAPE, "channel_stats: sumsq must follow sum by >= C doubles");
+    bool vec = vec_ok(C, {{x, ld}});
+    StatsOp<1> o1{x, ld}; StatsOp<4> o4{x, ld};
+    return launch_reduce(o1, o4, vec, C, npix, sum, (long long)(sumsq - sum), (cudaStream_t)stream, "channel_stats_kernel");
+}
+
+__global__ void add_d2f_kernel(const double* __restrict__ src, float* dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += (float)src[i];
+}
+extern "C" int saunet_add_d2f(const double* src, float* dst, int n, void* stream) {
+    SAUNET_CHECK_ARG(src && dst && n > 0, SAUNET_ERR_BAD_SHAPE, "add_d2f: bad args");
+    add_d2f_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(src, dst, n);
+    SAUNET_CHECK_LAUNCH("add_d2f_kernel");
+    return SAUNET_OK;
+}
+
+extern "C" int saunet_bn_finalize(const double* sum, const double* sumsq, double count, const float* gamma, const float* beta,
+                                  float* running_mean, float* running_var, float momentum, float eps, int training, int C,
+                                  float* state, void* stream) {
+    SAUNET_CHECK_ARG(C > 0 && state, SAUNET_ERR_BAD_SHAPE, "bn_finalize: bad args");
+    SAUNET_CHECK_ARG(training ? (sum && sumsq && count > 0) : (running_mean && running_var), SAUNET_ERR_BAD_SHAPE,
+                     "bn_finalize: missing statistics");
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sum, sumsq, count, gamma, beta, running_mean, running_var,
+                                                                       momentum, eps, training, C, state);
+    SAUNET_CHECK_LAUNCH("bn_finalize_kernel");
+    return SAUNET_OK;
+}
+
+extern "C" int saunet_affine_act(const float* x, int x_ld, const float* scale, const float* shift, const float* residual,
+                                 int r_ld, float* y, int y_ld, int C, long long npix, int act, void* stream) {
+    SAUNET_CHECK_ARG(x && y && C > 0 && npix > 0 && x_ld >= C && y_ld >= C, SAUNET_ERR_BAD_SHAPE, "affine_act: bad args");
+    SAUNET_CHECK_ARG((scale == nullptr) == (shift == nullptr), SAUNET_ERR_BAD_SHAPE, "affine_act: scale/shift mismatch");
+    bool vec = vec_ok(C, {{x, x_ld}, {y, y_ld}, {residual, r_ld}});
+    if (vec) affine_act_kernel<4><<<ew_blocks(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_ld, scale, shift, residual, r_ld, y, y_ld, C, npix, act);
+    else affine_act_kernel<1><<<ew_blocks(npix * C), 256, 0, (cudaStream_t)stream>>>(x, x_ld, scale, shift, residual, r_ld, y, y_ld, C, npix, act);
+    SAUNET_CHECK_LAUNCH("affine_act_kernel");
+    return SAUNET_OK;
+}
+
+extern "C" int saunet_bn_bwd_reduce(const float* dy, int dy_ld, const float* x, int x_ld, const float* out, int out_ld,
+                                    const float* state, int C, long long npix, int act, double* red, void* stream) {
+    SAUNET_CHECK_ARG(dy && x && state && red && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "bn_bwd_reduce: bad args");
+    bool vec = vec_ok(C, {{dy, dy_ld}, {x, x_ld}, {out, out_ld}});
+    BnBwdOp<1> o1{dy, dy_ld, x, x_ld, out, out_ld, state, C, act};
+    BnBwdOp<4> o4{dy, dy_ld, x, x_ld, out, out_ld, state, C, act};
+    return launch_reduce(o1, o4, vec, C, npix, red, (long long)C, (cudaStream_t)stream, "bn_bwd_reduce_kernel");
+}
+
+extern "C" int saunet_bn_bwd_apply(const float* dy, int dy_ld, const float* x, int x_ld, const float* out, int out_ld,
+                                   const float* state, const float* gamma, const double* red, int C, long long npix, int act,
+                                   int training, float* dx, int dx_ld, int dx_acc, float* dres, int dres_ld, int dres_acc,
+                                   float* dgamma, float* dbeta, void* stream) {
+    SAUNET_CHECK_ARG(dy && x && state && red && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "bn_bwd_apply: bad args");
+    SAUNET_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), SAUNET_ERR_BAD_SHAPE, "bn_bwd_apply: dgamma/dbeta mismatch");
+    bool vec = vec_ok(C, {{dy, dy_ld}, {x, x_ld}, {out, out_ld}, {dx, dx_ld}, {dres, dres_ld}});
+    if (vec) bn_bwd_apply_kernel<4><<<ew_blocks(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dy, dy_ld, x, x_ld, out, out_ld, state, gamma, red, C, npix, act, training, dx, dx_ld, dx_acc, dres, dres_ld, dres_acc, dgamma, dbeta);
+    else bn_bwd_apply_kernel<1><<<ew_blocks(npix * C), 256, 0, (cudaStream_t)stream>>>(dy, dy_ld, x, x_ld, out, out_ld, state, gamma, red, C, npix, act, training, dx, dx_ld, dx_acc, dres, dres_ld, dres_acc, dgamma, dbeta);
+    SAUNET_CHECK_LAUNCH("bn_bwd_apply_kernel");
+    return SAUNET_OK;
+}

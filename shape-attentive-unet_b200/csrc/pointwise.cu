@@ -1,0 +1,477 @@
+// pointwise.cu -- HBM-bound resampling / gating / layout kernels on NHWC fp32.
+#include "common.cuh"
+
+namespace saunet {
+
+static inline int ew_blocks(long long n) {
+    long long b = (n + 255) / 256; long long cap = (long long)kNumSMs * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+static inline bool vec4(int C, const void* a, int lda, const void* b = nullptr, int ldb = 0, const void* c = nullptr, int ldc = 0) {
+    if (C % 4) return false;
+    if (a && (!aligned16(a) || lda % 4)) return false;
+    if (b && (!aligned16(b) || ldb % 4)) return false;
+    if (c && (!aligned16(c) || ldc % 4)) return false;
+    return true;
+}
+
+template <int VEC> struct V;
+template <> struct V<1> {
+    float v[1];
+    __device__ static V load(const float* p) { V r; r.v[0] = __ldg(p); return r; }
+    __device__ static V loadrw(const float* p) { V r; r.v[0] = *p; return r; }
+    __device__ void store(float* p) const { p[0] = v[0]; }
+};
+template <> struct V<4> {
+    float v[4];
+    __device__ static V load(const float* p) { float4 t = __ldg(reinterpret_cast<const float4*>(p)); V r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r; }
+    __device__ static V loadrw(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); V r; r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w; return r; }
+    __device__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+// ---- bilinear, align_corners=True -----------------------------------------------------------------
+__device__ __forceinline__ void src_index(float scale, int o, int in, int& i0, int& i1, float& l0, float& l1) {
+    float s = scale * (float)o;
+    i0 = (int)s; if (i0 > in - 1) i0 = in - 1;
+    i1 = i0 + (i0 < in - 1 ? 1 : 0);
+    l1 = s - (float)i0; l0 = 1.f - l1;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) bilinear_fwd_kernel(const float* __restrict__ x, int x_ld, int B, int Hin, int Win, int C,
+                                                           float* __restrict__ y, int y_ld, int Hout, int Wout, float sh, float sw) {
+    const int L = C / VEC;
+    const long long n = (long long)B * Hout * Wout * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % L) * VEC; long long p = idx / L;
+        int ox = (int)(p % Wout); long long q = p / Wout; int oy = (int)(q % Hout); int b = (int)(q / Hout);
+        int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+        src_index(sh, oy, Hin, y0, y1, ly0, ly1);
+        src_index(sw, ox, Win, x0, x1, lx0, lx1);
+        const float* base = x + (size_t)b * Hin * Win * x_ld + c;
+        V<VEC> v00 = V<VEC>::load(base + ((size_t)y0 * Win + x0) * x_ld);
+        V<VEC> v01 = V<VEC>::load(base + ((size_t)y0 * Win + x1) * x_ld);
+        V<VEC> v10 = V<VEC>::load(base + ((size_t)y1 * Win + x0) * x_ld);
+        V<VEC> v11 = V<VEC>::load(base + ((size_t)y1 * Win + x1) * x_ld);
+        V<VEC> o;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            o.v[e] = ly0 * (lx0 * v00.v[e] + lx1 * v01.v[e]) + ly1 * (lx0 * v10.v[e] + lx1 * v11.v[e]);
+        o.store(y + (size_t)p * y_ld + c);
+    }
+}
+
+// gather form of the backward: every input pixel sums the output pixels that read it (deterministic,
+// no atomics, no memset).
+template <int VEC>
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restrict__ dy, int dy_ld, int B, int Hin, int Win, int C,
+                                                           float* dx, int dx_ld, int Hout, int Wout, float sh, float sw, int accumulate) {
+    const int L = C / VEC;
+    const long long n = (long long)B * Hin * Win * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % L) * VEC; long long p = idx / L;
+        int ix = (int)(p % Win); long long q = p / Win; int iy = (int)(q % Hin); int b = (int)(q / Hin);
+        int oylo = 0, oyhi = Hout - 1, oxlo = 0, oxhi = Wout - 1;
+        if (sh > 0.f) { oylo = max(0, (int)floorf((float)(iy - 1) / sh) - 1); oyhi = min(Hout - 1, (int)ceilf((float)(iy + 1) / sh) + 1); }
+        if (sw > 0.f) { oxlo = max(0, (int)floorf((float)(ix - 1) / sw) - 1); oxhi = min(Wout - 1, (int)ceilf((float)(ix + 1) / sw) + 1); }
+        float acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+        const float* base = dy + (size_t)b * Hout * Wout * dy_ld + c;
+        for (int oy = oylo; oy <= oyhi; ++oy) {
+            int y0, y1; float ly0, ly1;
+            src_index(sh, oy, Hin, y0, y1, ly0, ly1);
+            float wy = (y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f);
+            if (wy == 0.f) continue;
+            for (int ox = oxlo; ox <= oxhi; ++ox) {
+                int x0, x1; float lx0, lx1;
+                src_index(sw, ox, Win, x0, x1, lx0, lx1);
+                float wx = (x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f);
+                if (wx == 0.f) continue;
+                V<VEC> g = V<VEC>::load(base + ((size_t)oy * Wout + ox) * dy_ld);
+                float w = wy * wx;
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] = fmaf(w, g.v[e], acc[e]);
+            }
+        }
+        float* dp = dx + (size_t)p * dx_ld + c;
+        V<VEC> o;
+        if (accumulate) { o = V<VEC>::loadrw(dp);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) o.v[e] += acc[e]; }
+        else {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) o.v[e] = acc[e]; }
+        o.store(dp);
+    }
+}
+
+// ---- 2x2 pools ----------------------------------------------------------------------------------------
+template <int VEC, bool MAXP>
+__global__ void __launch_bounds__(256) pool2_fwd_kernel(const float* __restrict__ x, int x_ld, int B, int Hin, int Win, int C,
+                                                        float* __restrict__ y, int y_ld) {
+    const int L = C / VEC, Ho = Hin / 2, Wo = Win / 2;
+    const long long n = (long long)B * Ho * Wo * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % L) * VEC; long long p = idx / L;
+        int ox = (int)(p % Wo); long long q = p / Wo; int oy = (int)(q % Ho); int b = (int)(q / Ho);
+        const float* base = x + (((size_t)b * Hin + 2 * oy) * Win + 2 * ox) * x_ld + c;
+        V<VEC> a = V<VEC>::load(base), bb = V<VEC>::load(base + x_ld);
+        V<VEC> cc = V<VEC>::load(base + (size_t)Win * x_ld), dd = V<VEC>::load(base + (size_t)Win * x_ld + x_ld);
+        V<VEC> o;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            o.v[e] = MAXP ? fmaxf(fmaxf(a.v[e], bb.v[e]), fmaxf(cc.v[e], dd.v[e])) : ((a.v[e] + bb.v[e]) + (cc.v[e] + dd.v[e])) * 0.25f;
+        o.store(y + (size_t)p * y_ld + c);
+    }
+}
+template <int VEC, bool MAXP>
+__global__ void __launch_bounds__(256) pool2_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ x, int x_ld,
+                                                        int B, int Hin, int Win, int C, float* dx, int dx_ld, int accumulate) {
+    // one thread per INPUT pixel group so odd trailing rows/cols receive an explicit zero
+    const int L = C / VEC, Ho = Hin / 2, Wo = Win / 2;
+    const long long n = (long long)B * Hin * Win * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % L) * VEC; long long p = idx / L;
+        int ix = (int)(p % Win); long long q = p / Win; int iy = (int)(q % Hin); int b = (int)(q / Hin);
+        int oy = iy >> 1, ox = ix >> 1;
+        V<VEC> o;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o.v[e] = 0.f;
+        if (oy < Ho && ox < Wo) {
+            V<VEC> g = V<VEC>::load(dy + (((size_t)b * Ho + oy) * Wo + ox) * dy_ld + c);
+            if (MAXP) {
+                const float* base = x + (((size_t)b * Hin + 2 * oy) * Win + 2 * ox) * x_ld + c;
+                V<VEC> w[4] = {V<VEC>::load(base), V<VEC>::load(base + x_ld), V<VEC>::load(base + (size_t)Win * x_ld),
+                               V<VEC>::load(base + (size_t)Win * x_ld + x_ld)};
+                const int me = (iy & 1) * 2 + (ix & 1);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    int am = 0; float m = w[0].v[e];
+#pragma unroll
+                    for (int k = 1; k < 4; ++k) if (w[k].v[e] > m) { m = w[k].v[e]; am = k; }
+                    o.v[e] = (am == me) ? g.v[e] : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) o.v[e] = 0.25f * g.v[e];
+            }
+        }
+        float* dp = dx + (size_t)p * dx_ld + c;
+        if (accumulate) { V<VEC> t = V<VEC>::loadrw(dp);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) o.v[e] += t.v[e]; }
+        o.store(dp);
+    }
+}
+
+// ---- global average pool --------------------------------------------------------------------------------
+// grid (C/32, B, splits); block 256 = 8 pixel rows x 32 channel lanes; y pre-zeroed, float atomics.
+__global__ void __launch_bounds__(256) gap_fwd_kernel(const float* __restrict__ x, int x_ld, long long HW, int C, float* y, float inv) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane, b = blockIdx.y;
+    const long long per = (HW + gridDim.z - 1) / gridDim.z;
+    const long long p0 = blockIdx.z * per; long long p1 = p0 + per; if (p1 > HW) p1 = HW;
+    float acc = 0.f;
+    if (c < C) {
+        const float* base = x + (size_t)b * HW * x_ld + c;
+        for (long long p = p0 + r; p < p1; p += 8) acc += __ldg(base + (size_t)p * x_ld);
+    }
+    red[r][lane] = acc;
+    __syncthreads();
+    if (r == 0 && c < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][lane];
+        atomicAdd(y + (size_t)b * C + c, s * inv);
+    }
+}
+template <int VEC>
+__global__ void __launch_bounds__(256) gap_bwd_kernel(const float* __restrict__ dy, int B, long long HW, int C, float* dx, int dx_ld,
+                                                      int accumulate, float inv) {
+    const int L = C / VEC;
+    const long long n = (long long)B * HW * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(idx % L) * VEC; long long p = idx / L; int b = (int)(p / HW);
+        V<VEC> g = V<VEC>::load(dy + (size_t)b * C + c);
+        float* dp = dx + (size_t)p * dx_ld + c;
+        V<VEC> o;
+        if (accumulate) o = V<VEC>::loadrw(dp);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o.v[e] = (accumulate ? o.v[e] : 0.f) + g.v[e] * inv;
+        o.store(dp);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ y, int y_ld,
+                                                      float* dz, int dz_ld, int C, long long npix, int act) {
+    const int L = C / VEC;
+    const long long n = npix * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        long long p = idx / L; int c = (int)(idx - p * L) * VEC;
+        V<VEC> g = V<VEC>::load(dy + (size_t)p * dy_ld + c), yv = V<VEC>::load(y + (size_t)p * y_ld + c);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            if (act == SAUNET_ACT_SIGMOID) g.v[e] = g.v[e] * yv.v[e] * (1.f - yv.v[e]);
+            else if (act == SAUNET_ACT_RELU) g.v[e] = yv.v[e] > 0.f ? g.v[e] : 0.f;
+        }
+        g.store(dz + (size_t)p * dz_ld + c);
+    }
+}
+
+// ---- DualAttBlock combine -----------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) dualatt_fwd_kernel(const float* __restrict__ f, int f_ld, const float* __restrict__ S,
+                                                          const float* __restrict__ cv, long long HW, int C, long long npix,
+                                                          float* __restrict__ out, int o_ld) {
+    const int L = C / VEC;
+    const long long n = npix * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        long long p = idx / L; int c = (int)(idx - p * L) * VEC; int b = (int)(p / HW);
+        V<VEC> v = V<VEC>::load(f + (size_t)p * f_ld + c), cc = V<VEC>::load(cv + (size_t)b * C + c);
+        const float s1 = __ldg(S + p) + 1.f;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v.v[e] = s1 * (v.v[e] * cc.v[e]);
+        v.store(out + (size_t)p * o_ld + c);
+    }
+}
+// grid (chunks, B); block 256 = 8 warps; each warp walks pixels of image b, lanes walk channels.
+template <int MAXCH>
+__global__ void __launch_bounds__(256) dualatt_bwd_kernel(const float* __restrict__ dout, int do_ld, const float* __restrict__ f, int f_ld,
+                                                          const float* __restrict__ S, const float* __restrict__ cv, long long HW, int C,
+                                                          float* df, int df_ld, int df_acc, float* __restrict__ dS, float* dcv) {
+    __shared__ float red[8][32 * MAXCH + 1];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, b = blockIdx.y;
+    const long long per = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * per; long long p1 = p0 + per; if (p1 > HW) p1 = HW;
+    float accc[MAXCH], cvr[MAXCH];
+#pragma unroll
+    for (int k = 0; k < MAXCH; ++k) { accc[k] = 0.f; int c = k * 32 + lane; cvr[k] = c < C ? cv[(size_t)b * C + c] : 0.f; }
+    for (long long pl = p0 + w; pl < p1; pl += 8) {
+        const long long p = (long long)b * HW + pl;
+        const float s1 = __ldg(S + p) + 1.f;
+        float accS = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXCH; ++k) {
+            int c = k * 32 + lane;
+            if (c < C) {
+                float g = __ldg(dout + (size_t)p * do_ld + c), fv = __ldg(f + (size_t)p * f_ld + c);
+                float t = g * fv;
+                accS = fmaf(t, cvr[k], accS);
+                accc[k] = fmaf(t, s1, accc[k]);
+                float d = g * s1 * cvr[k];
+                float* dp = df + (size_t)p * df_ld + c;
+                *dp = df_acc ? *dp + d : d;
+            }
+        }
+        accS = warp_sum(accS);
+        if (lane == 0) dS[p] = accS;
+    }
+#pragma unroll
+    for (int k = 0; k < MAXCH; ++k) red[w][k * 32 + lane] = accc[k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * MAXCH; i += 256) {
+        if (i < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += red[k][i];
+            atomicAdd(dcv + (size_t)b * C + i, s);
+        }
+    }
+}
+
+// ---- GSConv gate backward --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rowscale_bwd_kernel(const float* __restrict__ dout, int do_ld, const float* __restrict__ out, int o_ld,
+                                                           const float* __restrict__ alpha, int C, long long npix, float* __restrict__ du,
+                                                           int du_ld, float* dalpha, int da_acc) {
+    // one warp per pixel, lanes over channels
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long p = warp; p < npix; p += nw) {
+        const float a1 = __ldg(alpha + p) + 1.f;
+        const float inv = 1.f / a1;
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            float g = __ldg(dout + (size_t)p * do_ld + c), o = __ldg(out + (size_t)p * o_ld + c);
+            du[(size_t)p * du_ld + c] = g * a1;
+            acc = fmaf(g, o * inv, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) dalpha[p] = da_acc ? dalpha[p] + acc : acc;
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) copy_slice_kernel(const float* __restrict__ src, int s_ld, float* dst, int d_ld, int C, long long npix, int accumulate) {
+    const int L = C / VEC;
+    const long long n = npix * L;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        long long p = idx / L; int c = (int)(idx - p * L) * VEC;
+        V<VEC> v = V<VEC>::load(src + (size_t)p * s_ld + c);
+        float* dp = dst + (size_t)p * d_ld + c;
+        if (accumulate) { V<VEC> o = V<VEC>::loadrw(dp);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v.v[e] += o.v[e]; }
+        v.store(dp);
+    }
+}
+
+// ---- layout conversion: 32x32 smem tile transpose per image -----------------------------------------------
+// TO_NHWC: src [B][C][HW] -> dst [B][HW][ld];  else src [B][HW][ld] -> dst [B][C][HW]
+template <bool TO_NHWC>
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int ld, int C, long long HW) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32; const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    if (TO_NHWC) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int c = c0 + ty + k * 8; long long p = p0 + tx;
+            tile[ty + k * 8][tx] = (c < C && p < HW) ? __ldg(src + ((size_t)b * C + c) * HW + p) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            long long p = p0 + ty + k * 8; int c = c0 + tx;
+            if (c < C && p < HW) dst[((size_t)b * HW + p) * ld + c] = tile[tx][ty + k * 8];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            long long p = p0 + ty + k * 8; int c = c0 + tx;
+            tile[ty + k * 8][tx] = (c < C && p < HW) ? __ldg(src + ((size_t)b * HW + p) * ld + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int c = c0 + ty + k * 8; long long p = p0 + tx;
+            if (c < C && p < HW) dst[((size_t)b * C + c) * HW + p] = tile[tx][ty + k * 8];
+        }
+    }
+}
+
+}  // namespace saunet
+
+using namespace saunet;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int saunet_bilinear_fwd(const float* x, int x_ld, int B, int Hin, int Win, int C, float* y, int y_ld, int Hout, int Wout, void* stream) {
+    SAUNET_CHECK_ARG(x && y && B > 0 && Hin > 0 && Win > 0 && C > 0 && Hout > 0 && Wout > 0, SAUNET_ERR_BAD_SHAPE, "bilinear_fwd: bad args");
+    float sh = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f, sw = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+    long long n = (long long)B * Hout * Wout;
+    if (vec4(C, x, x_ld, y, y_ld)) bilinear_fwd_kernel<4><<<ew_blocks(n * (C / 4)), 256, 0, ST>>>(x, x_ld, B, Hin, Win, C, y, y_ld, Hout, Wout, sh, sw);
+    else bilinear_fwd_kernel<1><<<ew_blocks(n * C), 256, 0, ST>>>(x, x_ld, B, Hin, Win, C, y, y_ld, Hout, Wout, sh, sw);
+    SAUNET_CHECK_LAUNCH("bilinear_fwd_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_bilinear_bwd(const float* dy, int dy_ld, int B, int Hin, int Win, int C, float* dx, int dx_ld, int Hout, int Wout, int accumulate, void* stream) {
+    SAUNET_CHECK_ARG(dy && dx && B > 0 && Hin > 0 && Win > 0 && C > 0 && Hout > 0 && Wout > 0, SAUNET_ERR_BAD_SHAPE, "bilinear_bwd: bad args");
+    float sh = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f, sw = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
+    long long n = (long long)B * Hin * Win;
+    if (vec4(C, dy, dy_ld, dx, dx_ld)) bilinear_bwd_kernel<4><<<ew_blocks(n * (C / 4)), 256, 0, ST>>>(dy, dy_ld, B, Hin, Win, C, dx, dx_ld, Hout, Wout, sh, sw, accumulate);
+    else bilinear_bwd_kernel<1><<<ew_blocks(n * C), 256, 0, ST>>>(dy, dy_ld, B, Hin, Win, C, dx, dx_ld, Hout, Wout, sh, sw, accumulate);
+    SAUNET_CHECK_LAUNCH("bilinear_bwd_kernel");
+    return SAUNET_OK;
+}
+
+template <bool MAXP>
+static int pool_fwd(const float* x, int x_ld, int B, int Hin, int Win, int C, float* y, int y_ld, void* stream) {
+    SAUNET_CHECK_ARG(x && y && B > 0 && Hin > 1 && Win > 1 && C > 0, SAUNET_ERR_BAD_SHAPE, "pool2_fwd: bad args");
+    long long n = (long long)B * (Hin / 2) * (Win / 2);
+    if (vec4(C, x, x_ld, y, y_ld)) pool2_fwd_kernel<4, MAXP><<<ew_blocks(n * (C / 4)), 256, 0, ST>>>(x, x_ld, B, Hin, Win, C, y, y_ld);
+    else pool2_fwd_kernel<1, MAXP><<<ew_blocks(n * C), 256, 0, ST>>>(x, x_ld, B, Hin, Win, C, y, y_ld);
+    SAUNET_CHECK_LAUNCH("pool2_fwd_kernel");
+    return SAUNET_OK;
+}
+template <bool MAXP>
+static int pool_bwd(const float* dy, int dy_ld, const float* x, int x_ld, int B, int Hin, int Win, int C, float* dx, int dx_ld, int accumulate, void* stream) {
+    SAUNET_CHECK_ARG(dy && dx && (!MAXP || x) && B > 0 && Hin > 1 && Win > 1 && C > 0, SAUNET_ERR_BAD_SHAPE, "pool2_bwd: bad args");
+    long long n = (long long)B * Hin * Win;
+    if (vec4(C, dy, dy_ld, dx, dx_ld, x, x_ld)) pool2_bwd_kernel<4, MAXP><<<ew_blocks(n * (C / 4)), 256, 0, ST>>>(dy, dy_ld, x, x_ld, B, Hin, Win, C, dx, dx_ld, accumulate);
+    else pool2_bwd_kernel<1, MAXP><<<ew_blocks(n * C), 256, 0, ST>>>(dy, dy_ld, x, x_ld, B, Hin, Win, C, dx, dx_ld, accumulate);
+    SAUNET_CHECK_LAUNCH("pool2_bwd_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_avgpool2_fwd(const float* x, int x_ld, int B, int Hin, int Win, int C, float* y, int y_ld, void* stream) { return pool_fwd<false>(x, x_ld, B, Hin, Win, C, y, y_ld, stream); }
+extern "C" int saunet_maxpool2_fwd(const float* x, int x_ld, int B, int Hin, int Win, int C, float* y, int y_ld, void* stream) { return pool_fwd<true>(x, x_ld, B, Hin, Win, C, y, y_ld, stream); }
+extern "C" int saunet_avgpool2_bwd(const float* dy, int dy_ld, int B, int Hin, int Win, int C, float* dx, int dx_ld, int accumulate, void* stream) { return pool_bwd<false>(dy, dy_ld, nullptr, 0, B, Hin, Win, C, dx, dx_ld, accumulate, stream); }
+extern "C" int saunet_maxpool2_bwd(const float* dy, int dy_ld, const float* x, int x_ld, int B, int Hin, int Win, int C, float* dx, int dx_ld, int accumulate, void* stream) { return pool_bwd<true>(dy, dy_ld, x, x_ld, B, Hin, Win, C, dx, dx_ld, accumulate, stream); }
+
+extern "C" int saunet_gap_fwd(const float* x, int x_ld, int B, long long HW, int C, float* y, void* stream) {
+    SAUNET_CHECK_ARG(x && y && B > 0 && HW > 0 && C > 0, SAUNET_ERR_BAD_SHAPE, "gap_fwd: bad args");
+    cudaError_t e = cudaMemsetAsync(y, 0, sizeof(float) * (size_t)B * C, ST);
+    SAUNET_CHECK_ARG(e == cudaSuccess, SAUNET_ERR_CUDA, "gap_fwd: memset failed: %s", cudaGetErrorString(e));
+    int cb = cdiv(C, 32);
+    long long splits = (long long)kNumSMs * 4 / ((long long)cb * B); if (splits < 1) splits = 1;
+    long long maxs = (HW + 63) / 64; if (splits > maxs) splits = maxs;
+    gap_fwd_kernel<<<dim3(cb, B, (unsigned)splits), 256, 0, ST>>>(x, x_ld, HW, C, y, 1.0f / (float)HW);
+    SAUNET_CHECK_LAUNCH("gap_fwd_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_gap_bwd(const float* dy, int B, long long HW, int C, float* dx, int dx_ld, int accumulate, void* stream) {
+    SAUNET_CHECK_ARG(dy && dx && B > 0 && HW > 0 && C > 0, SAUNET_ERR_BAD_SHAPE, "gap_bwd: bad args");
+    long long n = (long long)B * HW;
+    if (vec4(C, dy, C, dx, dx_ld)) gap_bwd_kernel<4><<<ew_blocks(n * (C / 4)), 256, 0, ST>>>(dy, B, HW, C, dx, dx_ld, accumulate, 1.0f / (float)HW);
+    else gap_bwd_kernel<1><<<ew_blocks(n * C), 256, 0, ST>>>(dy, B, HW, C, dx, dx_ld, accumulate, 1.0f / (float)HW);
+    SAUNET_CHECK_LAUNCH("gap_bwd_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_act_bwd(const float* dy, int dy_ld, const float* y, int y_ld, float* dz, int dz_ld, int C, long long npix, int act, void* stream) {
+    SAUNET_CHECK_ARG(dy && y && dz && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "act_bwd: bad args");
+    if (vec4(C, dy, dy_ld, y, y_ld, dz, dz_ld)) act_bwd_kernel<4><<<ew_blocks(npix * (C / 4)), 256, 0, ST>>>(dy, dy_ld, y, y_ld, dz, dz_ld, C, npix, act);
+    else act_bwd_kernel<1><<<ew_blocks(npix * C), 256, 0, ST>>>(dy, dy_ld, y, y_ld, dz, dz_ld, C, npix, act);
+    SAUNET_CHECK_LAUNCH("act_bwd_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_dualatt_combine_fwd(const float* fused, int f_ld, const float* S, const float* cvec, int B, long long HW, int C, float* out, int o_ld, void* stream) {
+    SAUNET_CHECK_ARG(fused && S && cvec && out && B > 0 && HW > 0 && C > 0, SAUNET_ERR_BAD_SHAPE, "dualatt_combine_fwd: bad args");
+    long long npix = (long long)B * HW;
+    if (vec4(C, fused, f_ld, out, o_ld, cvec, C)) dualatt_fwd_kernel<4><<<ew_blocks(npix * (C / 4)), 256, 0, ST>>>(fused, f_ld, S, cvec, HW, C, npix, out, o_ld);
+    else dualatt_fwd_kernel<1><<<ew_blocks(npix * C), 256, 0, ST>>>(fused, f_ld, S, cvec, HW, C, npix, out, o_ld);
+    SAUNET_CHECK_LAUNCH("dualatt_fwd_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_dualatt_combine_bwd(const float* dout, int do_ld, const float* fused, int f_ld, const float* S, const float* cvec, int B, long long HW, int C,
+                                          float* dfused, int df_ld, int df_acc, float* dS, float* dcvec, void* stream) {
+    SAUNET_CHECK_ARG(dout && fused && S && cvec && dfused && dS && dcvec && B > 0 && HW > 0 && C > 0, SAUNET_ERR_BAD_SHAPE, "dualatt_combine_bwd: bad args");
+    SAUNET_CHECK_ARG(C <= 1024, SAUNET_ERR_BAD_SHAPE, "dualatt_combine_bwd: C=%d > 1024 unsupported", C);
+    long long chunks = (long long)kNumSMs * 4 / B; if (chunks < 1) chunks = 1;
+    long long maxc = (HW + 31) / 32; if (chunks > maxc) chunks = maxc;
+    dim3 grid((unsigned)chunks, B);
+    if (C <= 64) dualatt_bwd_kernel<2><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
+    else if (C <= 128) dualatt_bwd_kernel<4><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
+    else if (C <= 256) dualatt_bwd_kernel<8><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
+    else if (C <= 512) dualatt_bwd_kernel<16><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
+    else dualatt_bwd_kernel<32><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
+    SAUNET_CHECK_LAUNCH("dualatt_bwd_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_rowscale_bwd(const float* dout, int do_ld, const float* out, int o_ld, const float* alpha, int C, long long npix, float* du, int du_ld, float* dalpha, int da_acc, void* stream) {
+    SAUNET_CHECK_ARG(dout && out && alpha && du && dalpha && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "rowscale_bwd: bad args");
+    rowscale_bwd_kernel<<<ew_blocks(npix * 32), 256, 0, ST>>>(dout, do_ld, out, o_ld, alpha, C, npix, du, du_ld, dalpha, da_acc);
+    SAUNET_CHECK_LAUNCH("rowscale_bwd_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_copy_slice(const float* src, int s_ld, float* dst, int d_ld, int C, long long npix, int accumulate, void* stream) {
+    SAUNET_CHECK_ARG(src && dst && C > 0 && npix > 0 && s_ld >= C && d_ld >= C, SAUNET_ERR_BAD_SHAPE, "copy_slice: bad args");
+    if (vec4(C, src, s_ld, dst, d_ld)) copy_slice_kernel<4><<<ew_blocks(npix * (C / 4)), 256, 0, ST>>>(src, s_ld, dst, d_ld, C, npix, accumulate);
+    else copy_slice_kernel<1><<<ew_blocks(npix * C), 256, 0, ST>>>(src, s_ld, dst, d_ld, C, npix, accumulate);
+    SAUNET_CHECK_LAUNCH("copy_slice_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_nchw_to_nhwc(const float* src, float* dst, int dst_ld, int B, int C, long long HW, void* stream) {
+    SAUNET_CHECK_ARG(src && dst && B > 0 && C > 0 && HW > 0 && dst_ld >= C && B <= 65535, SAUNET_ERR_BAD_SHAPE, "nchw_to_nhwc: bad args");
+    transpose_kernel<true><<<dim3(cdiv(HW, 32), cdiv(C, 32), B), 256, 0, ST>>>(src, dst, dst_ld, C, HW);
+    SAUNET_CHECK_LAUNCH("transpose_kernel");
+    return SAUNET_OK;
+}
+extern "C" int saunet_nhwc_to_nchw(const float* src, int src_ld, float* dst, int B, int C, long long HW, void* stream) {
+    SAUNET_CHECK_ARG(src && dst && B > 0 && C > 0 && HW > 0 && src_ld >= C && B <= 65535, SAUNET_ERR_BAD_SHAPE, "nhwc_to_nchw: bad args");
+    transpose_kernel<false><<<dim3(cdiv(HW, 32), cdiv(C, 32), B), 256, 0, ST>>>(src, dst, src_ld, C, HW);
+    SAUNET_CHECK_LAUNCH("transpose_kernel");
+    return SAUNET_OK;
+}

@@ -45,7 +45,7 @@ def import_reference():
 
 def load_synth():
     import importlib.util
-    spec = importlib.util.spec_from_file_location("saunet_synth", os.path.join(PKG, "synth.py"))
+    spec = importlib.util.spec_from_file_location("saunet_synth", os.path.join(PKG, "saunet_b200", "synth.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from helpers import load_golden, template_state_dict, rel_err, alias_map
-import synth
+from saunet_b200 import synth
 from oracle import saunet_oracle as O
 from oracle import canny as ocanny
 
