@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- SAUNet fwd + DualLoss + bwd throughput in 2-D slices/sec (BASELINE.json's metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+ours       one process per GPU (torchrun for N>1); each rank runs `--batch` 256x256 slices per step through the
+           reference-facing API (models.SegmentationModule(crit, unet)(feed_dict, epoch) -> loss.backward()), all
+           arithmetic in libsaunet_b200.so; gradients all-reduced over NCCL.  `value` = device-timed with inputs
+           resident in HBM; `e2e` = same call with the step's inputs copied from pinned host memory and the loss
+           read back every step.
+reference  the reference's algorithm on the host CPU (oracle/ port, torch CPU ops, all host threads): the
+           reported CPU baseline.  Rank 0 only.
+
+A step = zero grads -> SAUNet forward (train-mode BatchNorm, on-device Canny) -> DualLoss -> backward
+(+ gradient all-reduce when N>1).  Synthetic ACDC-shaped slices, deterministic random-init weights.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "shape-attentive-unet_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "2D slices/sec, SAUNet fwd+bwd 256x256x1->4-class (whole job, device-timed, max over ranks)"
+UNIT = "slices/s"
+FLOP_PER_SLICE = 216.13e9          # conv FLOPs fwd+bwd per 256x256 slice
+SIZE = 256
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_ours(dev, batch):
+    from models import SAUNet, SegmentationModule
+    from loss import DualLoss
+    from saunet_b200 import synth
+    from saunet_b200.parallel import GradArena
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        unet = SAUNet(num_classes=4, pretrained=False)
+    unet.load_state_dict(synth.synthetic_state_dict(unet.state_dict(), seed=0))
+    unet = unet.to(dev).train()
+    seg_mod = SegmentationModule(DualLoss(num_classes=4), unet, 4).to(dev).train()
+    arena = GradArena(unet)
+    return seg_mod, unet, arena
+
+
+def host_batch(batch, rank):
+    from saunet_b200 import synth
+    base = synth.synthetic_batch(min(batch, 4), SIZE, seed=304 + rank)
+    rep = (batch + base["image"].shape[0] - 1) // base["image"].shape[0]
+    d = {k: v.repeat((rep,) + (1,) * (v.dim() - 1))[:batch].contiguous().pin_memory() for k, v in base.items()}
+    return d
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from saunet_b200 import _C
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _C.load()
+    B = args.batch
+    seg_mod, unet, arena = build_ours(dev, B)
+    hb = host_batch(B, rank)
+    resident = {k: v.to(dev) for k, v in hb.items()}
+
+    def step(feed):
+        arena.zero()
+        loss, acc = seg_mod({"image": feed["image"], "mask": (feed["seg"], feed["edge"])}, 0)
+        loss.backward()
+        arena.all_reduce()
+        return loss
+
+    def step_e2e():
+        feed = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        return float(step(feed).item())
+
+    def timed(fn, iters):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _C.launch_count()
+    ms = timed(lambda: step(resident), args.steps)
+    launches = _C.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    value = world * B * args.steps / (ms / 1e3)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+
+    # ---- per-kernel roofline pass (one extra step, every C-ABI call bracketed by CUDA events) ----
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        _C.PROFILE = []
+        step(resident)
+        torch.cuda.synchronize()
+        prof, _C.PROFILE = _C.PROFILE, None
+        agg = {}
+        for name, a, b, fl, nb in prof:
+            t = a.elapsed_time(b)
+            e = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
+            e[0] += t; e[1] += 1; e[2] += fl; e[3] += nb
+        total = sum(e[0] for e in agg.values())
+        top = max(agg.items(), key=lambda kv: kv[1][0])
+        pk = peaks()
+        conv_ms = sum(agg[k][0] for k in agg if "conv2d" in k)
+        conv_fl = sum(agg[k][2] for k in agg if "conv2d" in k)
+        name, (t_ms, cnt, fl, nb) = top
+        if "conv2d" in name:
+            ach = fl / (t_ms / 1e3) / 1e12
+            roof = {"bound": "tensor", "kernel": name, "achieved": round(ach, 2), "peak": pk["tflops"], "unit": "TFLOP/s",
+                    "frac": round(ach / pk["tflops"], 4), "traffic": None, "launches": cnt,
+                    "avg_launch_ms": round(t_ms / cnt, 4), "share_of_step": round(t_ms / total, 3), "peak_src": pk["src"],
+                    "all_conv_tflops": round(conv_fl / (conv_ms / 1e3) / 1e12, 2),
+                    "note": "peak = measured dense bf16 cuBLAS; this path computes in fp32"}
+        else:
+            ach = nb / (t_ms / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": name, "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach / pk["hbm_gbs"], 4), "traffic": None, "launches": cnt,
+                    "avg_launch_ms": round(t_ms / cnt, 4), "share_of_step": round(t_ms / total, 3), "peak_src": pk["src"]}
+        roof["by_call_ms"] = {k: round(v[0], 2) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:8]}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu_base = cpu_baseline_sample(steps=2, batch=2)
+    if rank == 0:
+        h2d = sum(v.numel() * v.element_size() for v in hb.values())
+        out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "SAUNet fwd+DualLoss+bwd, batch %d/GPU, 256x256x3 fp32 slices -> 4 classes, "
+                                      "train-mode BN, on-device Canny (BASELINE configs[1])" % B,
+                          "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                          "l2": "per-step working set (activations >> 126 MB L2) exceeds L2; no explicit flush"},
+               "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                       "ms_per_step": round(ms_e2e / args.steps, 3)},
+               "gpu_launches": int(launches), "clocks": clocks,
+               "tensor_pipe_fraction": round(FLOP_PER_SLICE * value / world / (peaks()["tflops"] * 1e12), 4),
+               "roofline": roof, "cpu_baseline": cpu_base}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample(steps, batch, threads=None):
+    """The reference algorithm (oracle/ port: torch CPU ops) on the host cores: fwd + DualLoss + bwd."""
+    from oracle import saunet_oracle as O
+    from saunet_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import template_state_dict
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    w = synth.synthetic_state_dict(template_state_dict(), seed=0)
+    data = synth.synthetic_batch(batch, SIZE, seed=304)
+    O.train_step(w, data["image"][:1], data["seg"][:1], data["edge"][:1])        # warm-up
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(w, data["image"], data["seg"], data["edge"])
+    dt = time.perf_counter() - t0
+    return {"value": round(steps * batch / dt, 3), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "%d steps of batch %d (256x256) fwd+DualLoss+bwd, torch %s CPU ops, %.1f s" %
+                      (steps, batch, torch.__version__, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import saunet_oracle as O
+    from saunet_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import template_state_dict
+    threads = os.cpu_count()
+    torch.set_num_threads(threads)
+    batch = 2
+    w = synth.synthetic_state_dict(template_state_dict(), seed=0)
+    data = synth.synthetic_batch(batch, SIZE, seed=304)
+    for _ in range(max(1, min(args.warmup, 2))):
+        O.train_step(w, data["image"][:1], data["seg"][:1], data["edge"][:1])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.train_step(w, data["image"], data["seg"], data["edge"])
+    dt = time.perf_counter() - t0
+    v = round(args.steps * batch / dt, 3)
+    sample = "each step = batch %d of the 256x256 workload (bounded sample), %d host threads" % (batch, threads)
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "SAUNet fwd+DualLoss+bwd, 256x256x3 fp32 slices -> 4 classes, train-mode BN "
+                                  "(reference algorithm on host CPU)", "batch_per_step": batch},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

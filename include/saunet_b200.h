@@ -155,12 +155,14 @@ int saunet_nhwc_to_nchw(const float* src, int src_ld, float* dst, int B, int C, 
 /* ---- loss: loss.py:51-88 (dice_loss), :149-159 (DualLoss.forward) --------------------------------
  * logits NHWC [npix][C] (C <= 8), edge prob [npix], seg target int64 [npix], edge target float [npix].
  * acc = double[2 + 2*C + 1]: [0]=sum w*nll, [1]=sum w, [2..2+C)=I_c, [2+C..2+2C)=Card_c, [2+2C]=sum bce (caller zeroes)
- * finalize writes loss[0]=total, [1]=dice, [2]=ce, [3]=bce (float). */
+ * parts: bit0 = dice, bit1 = weighted CE, bit2 = edge BCE -- the terms summed into loss[0] and differentiated
+ * (DualLoss = 7; loss.dice_loss alone = 1).
+ * finalize writes loss[0]=total of the selected parts, [1]=dice, [2]=ce, [3]=bce (float). */
 int saunet_dual_loss_fwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
-                         long long npix, int C, const float* class_w, double* acc, float* loss, void* stream);
+                         long long npix, int C, const float* class_w, int parts, double* acc, float* loss, void* stream);
 int saunet_dual_loss_bwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
                          long long npix, int C, const float* class_w, const double* acc, const float* dloss,
-                         float* dlogits, int dl_ld, float* dedge, void* stream);
+                         float* dlogits, int dl_ld, float* dedge, int parts, void* stream);
 
 /* ---- Canny fusion: models/models.py:358-364 (np.mean(axis=1).astype(uint8) + cv2.Canny(im,10,100)) ----
  * x is the fp32 image, NCHW [B][C][H][W]; out is float [B][H][W] in {0,255}.

@@ -66,28 +66,33 @@ __global__ void __launch_bounds__(256) dual_loss_fwd_kernel(const float* __restr
     block_reduce_atomic<2 + 2 * kMaxC + 1>(v, acc, 2 + 2 * C + 1);
 }
 
-__global__ void dual_loss_finalize_kernel(const double* __restrict__ acc, long long npix, int C, int has_edge, float* loss) {
+__global__ void dual_loss_finalize_kernel(const double* __restrict__ acc, long long npix, int C, int has_edge, int parts, float* loss) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     double ce = acc[0] / acc[1];
     double d = 0.0;
     for (int c = 0; c < C; ++c) d += 2.0 * acc[2 + c] / (acc[2 + C + c] + (double)kDiceEps);
     double dice = 1.0 - d / C;
     double bce = has_edge ? acc[2 + 2 * C] / (double)npix : 0.0;
-    loss[0] = (float)(dice + ce + bce); loss[1] = (float)dice; loss[2] = (float)ce; loss[3] = (float)bce;
+    double total = 0.0;
+    if (parts & 1) total += dice;
+    if (parts & 2) total += ce;
+    if (parts & 4) total += bce;
+    loss[0] = (float)total; loss[1] = (float)dice; loss[2] = (float)ce; loss[3] = (float)bce;
 }
 
 __global__ void __launch_bounds__(256) dual_loss_bwd_kernel(const float* __restrict__ logits, int l_ld, const float* __restrict__ edge,
                                                             const long long* __restrict__ seg_t, const float* __restrict__ edge_t,
                                                             long long npix, int C, const float* __restrict__ cw, const double* __restrict__ acc,
                                                             const float* __restrict__ dloss, float* __restrict__ dlogits, int dl_ld,
-                                                            float* __restrict__ dedge) {
+                                                            float* __restrict__ dedge, int parts) {
     const float g = dloss ? dloss[0] : 1.f;
-    const float inv_w = (float)(1.0 / acc[1]);
+    const float inv_w = (parts & 2) ? (float)(1.0 / acc[1]) : 0.f;
+    const float dsel = (parts & 1) ? 1.f : 0.f;
     float k1[kMaxC], k2[kMaxC];     // dice: d/dprob_c = -(1/C) * ( 2*oh/(Card+eps) - 2*I/(Card+eps)^2 )
     for (int c = 0; c < C; ++c) {
         double den = acc[2 + C + c] + (double)kDiceEps;
-        k1[c] = (float)(-2.0 / (den * C));
-        k2[c] = (float)(2.0 * acc[2 + c] / (den * den * C));
+        k1[c] = dsel * (float)(-2.0 / (den * C));
+        k2[c] = dsel * (float)(2.0 * acc[2 + c] / (den * den * C));
     }
     const float inv_n = 1.f / (float)npix;
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(256) dual_loss_bwd_kernel(const float* __restr
         }
         if (edge) {
             const float pe = __ldg(edge + p), te = __ldg(edge_t + p);
-            dedge[p] = g * inv_n * (pe - te) / fmaxf((1.f - pe) * pe, 1e-12f);
+            dedge[p] = (parts & 4) ? g * inv_n * (pe - te) / fmaxf((1.f - pe) * pe, 1e-12f) : 0.f;
         }
     }
 }
@@ -114,26 +119,26 @@ __global__ void __launch_bounds__(256) dual_loss_bwd_kernel(const float* __restr
 using namespace saunet;
 
 extern "C" int saunet_dual_loss_fwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
-                                    long long npix, int C, const float* class_w, double* acc, float* loss, void* stream) {
+                                    long long npix, int C, const float* class_w, int parts, double* acc, float* loss, void* stream) {
     SAUNET_CHECK_ARG(logits && seg_t && acc && loss && npix > 0, SAUNET_ERR_BAD_SHAPE, "dual_loss_fwd: bad args");
     SAUNET_CHECK_ARG(C >= 2 && C <= kMaxC && l_ld >= C, SAUNET_ERR_BAD_SHAPE, "dual_loss_fwd: C=%d unsupported (2..8)", C);
     SAUNET_CHECK_ARG((edge == nullptr) == (edge_t == nullptr), SAUNET_ERR_BAD_SHAPE, "dual_loss_fwd: edge/edge_t mismatch");
     long long blocks = (npix + 255) / 256; if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     dual_loss_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, l_ld, edge, seg_t, edge_t, npix, C, class_w, acc);
     SAUNET_CHECK_LAUNCH("dual_loss_fwd_kernel");
-    dual_loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, npix, C, edge != nullptr, loss);
+    dual_loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, npix, C, edge != nullptr, parts, loss);
     SAUNET_CHECK_LAUNCH("dual_loss_finalize_kernel");
     return SAUNET_OK;
 }
 
 extern "C" int saunet_dual_loss_bwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
                                     long long npix, int C, const float* class_w, const double* acc, const float* dloss,
-                                    float* dlogits, int dl_ld, float* dedge, void* stream) {
+                                    float* dlogits, int dl_ld, float* dedge, int parts, void* stream) {
     SAUNET_CHECK_ARG(logits && seg_t && acc && dlogits && npix > 0, SAUNET_ERR_BAD_SHAPE, "dual_loss_bwd: bad args");
     SAUNET_CHECK_ARG(C >= 2 && C <= kMaxC && l_ld >= C && dl_ld >= C, SAUNET_ERR_BAD_SHAPE, "dual_loss_bwd: C=%d unsupported (2..8)", C);
     SAUNET_CHECK_ARG(!edge || (edge_t && dedge), SAUNET_ERR_BAD_SHAPE, "dual_loss_bwd: edge given without edge_t/dedge");
     long long blocks = (npix + 255) / 256; if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    dual_loss_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, l_ld, edge, seg_t, edge_t, npix, C, class_w, acc, dloss, dlogits, dl_ld, dedge);
+    dual_loss_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, l_ld, edge, seg_t, edge_t, npix, C, class_w, acc, dloss, dlogits, dl_ld, dedge, parts);
     SAUNET_CHECK_LAUNCH("dual_loss_bwd_kernel");
     return SAUNET_OK;
 }

@@ -61,8 +61,8 @@ SIGNATURES = {
     "saunet_copy_slice": [_P, _I, _P, _I, _I, _L, _I, _P],
     "saunet_nchw_to_nhwc": [_P, _P, _I, _I, _I, _L, _P],
     "saunet_nhwc_to_nchw": [_P, _I, _P, _I, _I, _L, _P],
-    "saunet_dual_loss_fwd": [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P, _P],
-    "saunet_dual_loss_bwd": [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _P],
+    "saunet_dual_loss_fwd": [_P, _I, _P, _P, _P, _L, _I, _P, _I, _P, _P, _P],
+    "saunet_dual_loss_bwd": [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _I, _P],
     "saunet_canny_fwd": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],
 }
 _SPECIAL = {
@@ -108,8 +108,21 @@ def check(rc, name="saunet"):
         raise SaunetError("%s failed (%d): %s" % (name, rc, msg.decode() if msg else "?"))
 
 
-def call(name, *args):
-    rc = getattr(load(), name)(*args)
+# When set to a list, every call is bracketed by CUDA events on the current stream and appended as
+# (name, start_event, end_event, flops, bytes): bench.py's per-kernel roofline pass.  None on the normal path.
+PROFILE = None
+
+
+def call(name, *args, flops=0, nbytes=0):
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(load(), name)(*args)
+        e1.record()
+        PROFILE.append((name, e0, e1, flops, nbytes))
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != 0:
         check(rc, name)
 

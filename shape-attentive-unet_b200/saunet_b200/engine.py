@@ -1,0 +1,481 @@
+"""Host-side execution engine for the SAUNet hot path.
+
+Activations live in NHWC fp32 device buffers (``Buf`` = a channel slice of a
+``Store``); every arithmetic step is one call into libsaunet_b200.so through
+``_C.call``.  A ``Tape`` records one backward closure per forward step, so a
+whole model (or a single block) runs as ONE ``torch.autograd.Function`` whose
+backward replays the tape in reverse: fwd+bwd are hand-written per block, torch
+autograd only sees the module boundary.
+
+torch is used here for device memory (caching allocator), the current stream
+and the autograd boundary -- never for arithmetic on the path.  There is no CPU
+fallback: a non-CUDA tensor or a missing library raises.
+"""
+import ctypes
+
+import torch
+
+from . import _C
+from ._C import ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, WgradDesc
+
+BN_EPS = 1e-5
+
+
+def _round4(n):
+    return (n + 3) // 4 * 4
+
+
+class Store:
+    """One NHWC allocation [npix, ld] plus (lazily) its gradient twin."""
+    __slots__ = ("t", "g", "ld", "npix")
+
+    def __init__(self, t, npix, ld):
+        self.t, self.g, self.ld, self.npix = t, None, ld, npix
+
+
+class Buf:
+    """Channels [c0, c0+C) of a Store, viewed as a [B,H,W,C] feature map."""
+    __slots__ = ("s", "c0", "C", "B", "H", "W")
+
+    def __init__(self, s, c0, C, B, H, W):
+        self.s, self.c0, self.C, self.B, self.H, self.W = s, c0, C, B, H, W
+
+    @property
+    def ptr(self):
+        return self.s.t.data_ptr() + 4 * self.c0
+
+    @property
+    def ld(self):
+        return self.s.ld
+
+    @property
+    def npix(self):
+        return self.B * self.H * self.W
+
+    def slice(self, c0, C):
+        assert 0 <= c0 and c0 + C <= self.C
+        return Buf(self.s, self.c0 + c0, C, self.B, self.H, self.W)
+
+    def full(self):
+        return self.c0 == 0 and self.C == self.s.ld
+
+    def nchw(self):
+        """Zero-copy NCHW-shaped (channels_last-strided) tensor view."""
+        v = self.s.t.view(self.B, self.H, self.W, self.s.ld)
+        if not self.full():
+            v = v[..., self.c0:self.c0 + self.C]
+        return v.permute(0, 3, 1, 2)
+
+
+class Tape:
+    def __init__(self, device, record):
+        if device.type != "cuda":
+            raise RuntimeError("saunet_b200 runs on CUDA devices only (got %s); there is no CPU fallback" % device)
+        _C.load()
+        self.device = device
+        self.record = record
+        self.stream = torch.cuda.current_stream(device).cuda_stream
+        self.ops = []
+        self.pgrads = {}
+        self._dchunk = None
+        self._doff = 0
+        self._fchunk = None
+        self._foff = 0
+        self._keep = []
+        self.bn_tracked = []
+        self.arena = None
+
+    # ---- memory ---------------------------------------------------------
+    def new(self, B, H, W, C, ld=None):
+        ld = C if ld is None else ld
+        t = torch.empty(B * H * W * ld, dtype=torch.float32, device=self.device)
+        return Buf(Store(t, B * H * W, ld), 0, C, B, H, W)
+
+    def wrap(self, t, B, H, W, C):
+        """Adopt an existing contiguous [B,H,W,C] fp32 tensor."""
+        return Buf(Store(t, B * H * W, C), 0, C, B, H, W)
+
+    def dzeros(self, n):
+        """n zeroed doubles -> device pointer (arena; one memset per chunk)."""
+        n = (n + 1) // 2 * 2
+        if self._dchunk is None or self._doff + n > self._dchunk.numel():
+            self._dchunk = torch.zeros(max(1 << 15, n), dtype=torch.float64, device=self.device)
+            self._keep.append(self._dchunk)
+            self._doff = 0
+        p = self._dchunk.data_ptr() + 8 * self._doff
+        self._doff += n
+        return p
+
+    def fempty(self, n):
+        n = _round4(n)
+        if self._fchunk is None or self._foff + n > self._fchunk.numel():
+            self._fchunk = torch.empty(max(1 << 16, n), dtype=torch.float32, device=self.device)
+            self._keep.append(self._fchunk)
+            self._foff = 0
+        p = self._fchunk.data_ptr() + 4 * self._foff
+        self._foff += n
+        return p
+
+    def scratch(self, n):
+        t = torch.empty(n, dtype=torch.float32, device=self.device)
+        return t
+
+    # ---- gradients --------------------------------------------------------
+    def grad(self, buf):
+        """Existing gradient of ``buf`` (a Buf over the grad Store) or None."""
+        g = buf.s.g
+        if g is None:
+            return None
+        return Buf(g, buf.c0, buf.C, buf.B, buf.H, buf.W)
+
+    def gw(self, buf):
+        """Gradient write target for ``buf`` -> (gbuf, accumulate_flag).
+        First write covering the whole Store skips the zero fill."""
+        s = buf.s
+        if s.g is None:
+            if buf.full():
+                s.g = Store(torch.empty(s.npix * s.ld, dtype=torch.float32, device=self.device), s.npix, s.ld)
+                return Buf(s.g, buf.c0, buf.C, buf.B, buf.H, buf.W), 0
+            s.g = Store(torch.zeros(s.npix * s.ld, dtype=torch.float32, device=self.device), s.npix, s.ld)
+        return Buf(s.g, buf.c0, buf.C, buf.B, buf.H, buf.W), 1
+
+    def seed(self, buf, gt):
+        """Install an incoming NHWC-contiguous gradient tensor as buf's grad."""
+        s = buf.s
+        assert buf.full() and s.g is None
+        s.g = Store(gt, s.npix, s.ld)
+
+    def pgrad(self, p):
+        """Device pointer gradients of parameter ``p`` are accumulated into: a view of the module's flat
+        GradArena when one is attached (saunet_b200.parallel), else a per-parameter zero tensor handed to autograd."""
+        if self.arena is not None:
+            ptr = self.arena.ptr(p)
+            if ptr is not None:
+                return ptr
+        g = self.pgrads.get(p)
+        if g is None:
+            g = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            self.pgrads[p] = g
+        return g.data_ptr()
+
+    def backward(self):
+        for fn in reversed(self.ops):
+            fn()
+        self.ops = []
+
+    def on_backward(self, fn):
+        if self.record:
+            self.ops.append(fn)
+
+
+# ---------------------------------------------------------------------------
+# weight packing cache: (id(param), mode) -> (version, data_ptr, packed tensor)
+_PACK = {}
+
+
+def packed(tp, w, mode, A=None, Bc=None):
+    """Packed GEMM layout of a conv / conv-transpose weight (see saunet_pack_weights)."""
+    key = (id(w), mode)
+    ent = _PACK.get(key)
+    if ent is not None and ent[0] == w._version and ent[1] == w.data_ptr() and ent[2].device == w.device:
+        return ent[2].data_ptr()
+    if not w.is_contiguous():
+        raise RuntimeError("saunet_b200: conv weights must be contiguous")
+    a, b, kh, kw = w.shape
+    out = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
+    _C.call("saunet_pack_weights", w.data_ptr(), out.data_ptr(), a, b, kh, kw, mode, tp.stream)
+    _PACK[key] = (w._version, w.data_ptr(), out)
+    return out.data_ptr()
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+# ---------------------------------------------------------------------------
+# thin op wrappers
+def conv(tp, x, wptr, Cout, KH, KW, y, Hg, Wg, sy=1, sx=1, offy=0, offx=0, osy=1, osx=1, oy0=0, ox0=0,
+         pro=0, pro_relu=0, bias=0, row_scale=0, row_add=0.0, act=ACT_NONE, acc=0, stat=None):
+    d = ConvDesc()
+    d.x, d.x_ld, d.B, d.Hin, d.Win, d.Cin = x.ptr, x.ld, x.B, x.H, x.W, x.C
+    d.w, d.Cout, d.KH, d.KW = wptr, Cout, KH, KW
+    d.Hg, d.Wg, d.sy, d.sx, d.offy, d.offx = Hg, Wg, sy, sx, offy, offx
+    d.y, d.y_ld, d.Hout, d.Wout, d.osy, d.osx, d.oy0, d.ox0 = y.ptr, y.ld, y.H, y.W, osy, osx, oy0, ox0
+    if pro:
+        d.in_scale, d.in_shift, d.in_relu = pro, pro + 4 * x.C, pro_relu
+    else:
+        d.in_scale, d.in_shift, d.in_relu = None, None, 0
+    d.bias = bias or None
+    d.row_scale, d.row_scale_add = row_scale or None, row_add
+    d.act, d.accumulate = act, acc
+    if stat is not None:
+        d.stat_sum, d.stat_sumsq = stat
+    else:
+        d.stat_sum, d.stat_sumsq = None, None
+    M = x.B * Hg * Wg
+    _C.call("saunet_conv2d_fwd", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * x.C * Cout,
+            nbytes=4.0 * (x.npix * x.C + M * Cout + KH * KW * x.C * Cout))
+
+
+def wgrad(tp, p, q, dwptr, KH, KW, Hg, Wg, sy=1, sx=1, offy=0, offx=0, pro=0, pro_relu=0):
+    d = WgradDesc()
+    d.p, d.p_ld, d.Ca = p.ptr, p.ld, p.C
+    d.q, d.q_ld, d.Cb, d.B, d.Hq, d.Wq = q.ptr, q.ld, q.C, q.B, q.H, q.W
+    d.KH, d.KW, d.Hg, d.Wg, d.sy, d.sx, d.offy, d.offx = KH, KW, Hg, Wg, sy, sx, offy, offx
+    if pro:
+        d.q_scale, d.q_shift, d.q_relu = pro, pro + 4 * q.C, pro_relu
+    else:
+        d.q_scale, d.q_shift, d.q_relu = None, None, 0
+    d.dw = dwptr
+    M = q.B * Hg * Wg
+    _C.call("saunet_conv2d_wgrad", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * p.C * q.C,
+            nbytes=4.0 * M * (p.C + q.C))
+
+
+def channel_stats(tp, x, sum_ptr, sumsq_ptr):
+    _C.call("saunet_channel_stats", x.ptr, x.ld, x.C, x.npix, sum_ptr, sumsq_ptr, tp.stream)
+
+
+def affine_act(tp, x, state, y, act=ACT_NONE, res=None):
+    _C.call("saunet_affine_act", x.ptr, x.ld, state or None, (state + 4 * x.C) if state else None,
+            res.ptr if res is not None else None, res.ld if res is not None else 0, y.ptr, y.ld, x.C, x.npix, act,
+            tp.stream)
+
+
+def act_bwd(tp, dy, y, dz, act):
+    _C.call("saunet_act_bwd", dy.ptr, dy.ld, y.ptr, y.ld, dz.ptr, dz.ld, dy.C, dy.npix, act, tp.stream)
+
+
+def copy_slice(tp, src, dst, acc=0):
+    _C.call("saunet_copy_slice", src.ptr, src.ld, dst.ptr, dst.ld, src.C, src.npix, acc, tp.stream)
+
+
+def bias_grad(tp, dy, bias_param):
+    """d(bias)[c] += sum over pixels of dy[:, c] (fp64 column sums)."""
+    s = tp.dzeros(2 * dy.C)
+    channel_stats(tp, dy, s, s + 8 * dy.C)
+    _C.call("saunet_add_d2f", s, tp.pgrad(bias_param), dy.C, tp.stream)
+
+
+# ---------------------------------------------------------------------------
+class BN:
+    """One BatchNorm application: finalised state [scale, shift, mean, invstd] + what backward needs."""
+    __slots__ = ("mod", "state", "C", "training", "count")
+
+
+def bn_stats_slot(tp, C):
+    """(sum_ptr, sumsq_ptr) for C channels, zeroed."""
+    s = tp.dzeros(2 * C)
+    return (s, s + 8 * C)
+
+
+def bn_finalize(tp, mod, C, stat, count):
+    """Finalise a BatchNorm layer (nn.BatchNorm2d semantics):
+    training -> batch statistics from (sum, sumsq, count) + running-stat update;
+    eval -> running statistics."""
+    bn = BN()
+    bn.mod, bn.C, bn.count = mod, C, count
+    bn.training = bool(mod.training or not mod.track_running_stats)
+    bn.state = tp.fempty(4 * C)
+    upd = mod.training and mod.track_running_stats and mod.running_mean is not None
+    mom = mod.momentum
+    if upd and mom is None:
+        mom = 1.0 / float(int(mod.num_batches_tracked) + 1)
+    if bn.training:
+        assert stat is not None
+        _C.call("saunet_bn_finalize", stat[0], stat[1], float(count), _p(mod.weight), _p(mod.bias),
+                mod.running_mean.data_ptr() if upd else None, mod.running_var.data_ptr() if upd else None,
+                float(mom or 0.0), float(mod.eps), 1, C, bn.state, tp.stream)
+        if upd and mod.num_batches_tracked is not None:
+            tp.bn_tracked.append(mod.num_batches_tracked)
+    else:
+        _C.call("saunet_bn_finalize", None, None, 1.0, _p(mod.weight), _p(mod.bias), mod.running_mean.data_ptr(),
+                mod.running_var.data_ptr(), 0.0, float(mod.eps), 0, C, bn.state, tp.stream)
+    return bn
+
+
+def bn_backward(tp, bn, dy, x, out, act, dx, dx_acc, dres=None, dres_acc=0):
+    """Two-pass BN(+ReLU) backward.  ``out`` (post-activation tensor) supplies the ReLU mask when it was
+    materialised, else the mask is recomputed from x.  dx may alias dy."""
+    C = bn.C
+    red = tp.dzeros(2 * C)
+    _C.call("saunet_bn_bwd_reduce", dy.ptr, dy.ld, x.ptr, x.ld, out.ptr if out is not None else None,
+            out.ld if out is not None else 0, bn.state, C, dy.npix, act, red, tp.stream)
+    mod = bn.mod
+    has_affine = mod.weight is not None
+    _C.call("saunet_bn_bwd_apply", dy.ptr, dy.ld, x.ptr, x.ld, out.ptr if out is not None else None,
+            out.ld if out is not None else 0, bn.state, _p(mod.weight), red, C, dy.npix, act, 1 if bn.training else 0,
+            dx.ptr if dx is not None else None, dx.ld if dx is not None else 0, dx_acc,
+            dres.ptr if dres is not None else None, dres.ld if dres is not None else 0, dres_acc,
+            tp.pgrad(mod.weight) if has_affine else None, tp.pgrad(mod.bias) if has_affine else None, tp.stream)
+
+
+# ---------------------------------------------------------------------------
+# composite: a convolution layer (nn.Conv2d semantics, stride 1 or 2, "same"-style padding) with its backward
+class ConvRec:
+    __slots__ = ("x", "y", "w", "b", "k", "stride", "pad", "pro", "pro_relu")
+
+
+def conv2d(tp, x, w, b, y=None, stride=1, pad=0, pro=None, pro_relu=0, act=ACT_NONE, stat=None, row_scale=0,
+           row_add=0.0):
+    """y = act(rowscale * (conv(prologue(x), w) + b)); returns (y, rec) -- rec feeds conv2d_bwd."""
+    Cout, Cin, KH, KW = w.shape
+    assert Cin == x.C, "conv2d: weight expects %d input channels, got %d" % (Cin, x.C)
+    Ho = (x.H + 2 * pad - KH) // stride + 1
+    Wo = (x.W + 2 * pad - KW) // stride + 1
+    if y is None:
+        y = tp.new(x.B, Ho, Wo, Cout)
+    assert (y.H, y.W, y.C) == (Ho, Wo, Cout)
+    conv(tp, x, packed(tp, w, 0), Cout, KH, KW, y, Ho, Wo, sy=stride, sx=stride, offy=-pad, offx=-pad,
+         pro=pro.state if pro is not None else 0, pro_relu=pro_relu, bias=_p(b), row_scale=row_scale, row_add=row_add,
+         act=act, stat=stat)
+    r = ConvRec()
+    r.x, r.y, r.w, r.b, r.k, r.stride, r.pad, r.pro, r.pro_relu = x, y, w, b, (KH, KW), stride, pad, pro, pro_relu
+    return y, r
+
+
+def conv2d_bwd(tp, r, dy, dx=None, dx_acc=0, need_bias=True):
+    """Given dy = d loss / d (conv output incl. bias): weight grad, bias grad and (if dx given) data grad
+    w.r.t. the PROLOGUE OUTPUT (i.e. the activated tensor the GEMM consumed)."""
+    w, x = r.w, r.x
+    Cout, Cin, KH, KW = w.shape
+    if w.requires_grad:
+        dwp = torch.zeros(w.numel(), dtype=torch.float32, device=tp.device)
+        wgrad(tp, dy, x, dwp.data_ptr(), KH, KW, dy.H, dy.W, sy=r.stride, sx=r.stride, offy=-r.pad, offx=-r.pad,
+              pro=r.pro.state if r.pro is not None else 0, pro_relu=r.pro_relu)
+        _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cout, Cin, KH, KW, 1, tp.stream)
+    if r.b is not None and r.b.requires_grad and need_bias:
+        bias_grad(tp, dy, r.b)
+    if dx is not None:
+        if r.stride != 1:
+            raise RuntimeError("saunet_b200: data gradient of a strided conv is not on the SAUNet path")
+        conv(tp, dy, packed(tp, w, 1), Cin, KH, KW, dx, x.H, x.W, offy=-(KH - 1 - r.pad), offx=-(KW - 1 - r.pad),
+             acc=dx_acc)
+
+
+# ---- ConvTranspose2d k4 s2 p1 (attention_blocks.py:179-183, models.py:211) as 4 output phases ----------
+def convT4(tp, x, w, b, y, stat=None):
+    Cin, Cout, KH, KW = w.shape
+    assert (KH, KW) == (4, 4) and Cin == x.C and y.C == Cout and y.H == 2 * x.H and y.W == 2 * x.W
+    wp = packed(tp, w, 2)
+    for pa in range(2):
+        for pb in range(2):
+            ph = pa * 2 + pb
+            conv(tp, x, wp + 4 * ph * (4 * Cin * Cout), Cout, 2, 2, y, x.H, x.W, offy=pa - 1, offx=pb - 1, osy=2, osx=2,
+                 oy0=pa, ox0=pb, bias=_p(b), stat=stat)
+
+
+def convT4_bwd(tp, x, w, b, dy, dx, dx_acc):
+    Cin, Cout, _, _ = w.shape
+    if w.requires_grad:
+        dwp = torch.zeros(w.numel(), dtype=torch.float32, device=tp.device)
+        wgrad(tp, x, dy, dwp.data_ptr(), 4, 4, x.H, x.W, sy=2, sx=2, offy=-1, offx=-1)
+        _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cin, Cout, 4, 4, 1, tp.stream)
+    if b is not None and b.requires_grad:
+        bias_grad(tp, dy, b)
+    if dx is not None:
+        conv(tp, dy, packed(tp, w, 0), Cin, 4, 4, dx, x.H, x.W, sy=2, sx=2, offy=-1, offx=-1, acc=dx_acc)
+
+
+# ---- resampling / pooling ------------------------------------------------------------------------------
+def bilinear(tp, x, y):
+    _C.call("saunet_bilinear_fwd", x.ptr, x.ld, x.B, x.H, x.W, x.C, y.ptr, y.ld, y.H, y.W, tp.stream)
+
+    def bwd():
+        dy = tp.grad(y)
+        if dy is None:
+            return
+        dx, acc = tp.gw(x)
+        _C.call("saunet_bilinear_bwd", dy.ptr, dy.ld, x.B, x.H, x.W, x.C, dx.ptr, dx.ld, y.H, y.W, acc, tp.stream)
+    tp.on_backward(bwd)
+    return y
+
+
+def to_nhwc(tp, t):
+    """NCHW-shaped fp32 CUDA tensor -> Buf (zero-copy when already channels_last)."""
+    B, C, H, W = t.shape
+    if t.dtype != torch.float32:
+        raise RuntimeError("saunet_b200: fp32 tensors expected, got %s" % t.dtype)
+    v = t.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return tp.wrap(v.reshape(-1), B, H, W, C)
+    tc = t.contiguous()
+    out = tp.new(B, H, W, C)
+    _C.call("saunet_nchw_to_nhwc", tc.data_ptr(), out.ptr, out.ld, B, C, H * W, tp.stream)
+    tp._keep.append(tc)
+    return out
+
+
+def grad_to_nhwc(tp, g):
+    """Incoming NCHW-shaped gradient -> contiguous NHWC flat tensor (zero-copy when channels_last)."""
+    B, C, H, W = g.shape
+    v = g.permute(0, 2, 3, 1)
+    if v.is_contiguous() and g.dtype == torch.float32:
+        return v.reshape(-1)
+    gc = g.to(torch.float32).contiguous()
+    out = torch.empty(B * H * W * C, dtype=torch.float32, device=g.device)
+    _C.call("saunet_nchw_to_nhwc", gc.data_ptr(), out.data_ptr(), C, B, C, H * W, tp.stream)
+    tp._keep.append(gc)
+    return out
+
+
+# ---------------------------------------------------------------------------
+class _TapeFn(torch.autograd.Function):
+    """The module boundary: forward runs ``body(tape, *input_bufs)`` -> list of output Bufs; backward seeds the
+    output grads, replays the tape and hands back input and parameter gradients."""
+
+    @staticmethod
+    def forward(ctx, body, arena, n_in, *args):
+        ins, params = args[:n_in], args[n_in:]
+        dev = ins[0].device
+        record = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or any(t.requires_grad for t in ins))
+        tp = Tape(dev, record)
+        tp.arena = arena
+        in_bufs = [to_nhwc(tp, t.detach()) for t in ins]
+        outs = body(tp, *in_bufs)
+        if tp.bn_tracked:
+            torch._foreach_add_(tp.bn_tracked, 1)
+        ctx.tp, ctx.in_bufs, ctx.outs, ctx.params = tp, in_bufs, outs, params
+        ctx.in_need = [t.requires_grad for t in ins]
+        res = tuple(o.nchw() for o in outs)
+        if not record:
+            ctx.tp = None
+            ctx.in_bufs = ctx.outs = None
+        return res
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        tp = ctx.tp
+        if tp is None:
+            raise RuntimeError("saunet_b200: backward through a forward that did not record a tape")
+        tp.stream = torch.cuda.current_stream(tp.device).cuda_stream
+        for o, g in zip(ctx.outs, gouts):
+            if g is None:
+                continue
+            gt = grad_to_nhwc(tp, g)
+            if o.full() and o.s.g is None:
+                tp.seed(o, gt)
+            else:
+                gb, acc = tp.gw(o)
+                copy_slice(tp, Buf(Store(gt, o.npix, o.C), 0, o.C, o.B, o.H, o.W), gb, acc)
+        tp.backward()
+        gin = []
+        for b, need in zip(ctx.in_bufs, ctx.in_need):
+            g = tp.grad(b) if need else None
+            gin.append(g.nchw() if g is not None else None)
+        gp = [tp.pgrads.get(p) if p.requires_grad else None for p in ctx.params]
+        ctx.tp = ctx.in_bufs = ctx.outs = None
+        return (None, None, None) + tuple(gin) + tuple(gp)
+
+
+def run(module, body, inputs):
+    """Run ``body`` under one tape with ``module``'s parameters as autograd leaves."""
+    seen, params = set(), []
+    for p in module.parameters():
+        if id(p) not in seen:
+            seen.add(id(p))
+            params.append(p)
+    for t in inputs:
+        if not t.is_cuda:
+            raise RuntimeError("saunet_b200: input tensors must be CUDA tensors; there is no CPU fallback")
+    return _TapeFn.apply(body, getattr(module, "_saunet_grad_arena", None), len(inputs), *inputs, *params)

@@ -1,0 +1,80 @@
+"""CPU-side checks of the drop-in boundary: the state_dict / module-tree contract of the reference, the C-ABI
+library's exported symbols, and that the product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+import warnings
+
+import pytest
+import torch
+
+from helpers import ROOT, key_contract
+
+
+def _model():
+    from models import SAUNet
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return SAUNet(num_classes=4, pretrained=False)
+
+
+def test_state_dict_contract_matches_reference():
+    d = key_contract()
+    m = _model()
+    sd = m.state_dict()
+    ref = [(k["key"], tuple(k["shape"]), k["dtype"]) for k in d["keys"]]
+    mine = [(k, tuple(v.shape), str(v.dtype).replace("torch.", "")) for k, v in sd.items()]
+    assert mine == ref
+    assert [n for n, _ in m.named_children()] == d["children"]
+    assert [k for k, _ in m.named_parameters()] == d["param_names"]
+    assert sum(p.numel() for p in m.parameters()) == d["n_params"] == 32896505
+    # aliases share storage (models/models.py:304-313)
+    assert sd["conv1.0.weight"].data_ptr() == sd["encoder.features.conv0.weight"].data_ptr()
+    assert sd["conv5.1.running_var"].data_ptr() == sd["encoder.features.norm5.running_var"].data_ptr()
+
+
+def test_module_types_seen_by_train_py():
+    """train.py:166-185 (group_weight) sorts parameters by isinstance checks on these torch classes."""
+    from torch.nn.modules.batchnorm import _BatchNorm
+    from torch.nn.modules.conv import _ConvNd
+    from models.GSConv import GatedSpatialConv2d
+    m = _model()
+    assert isinstance(m.gate1, _ConvNd) and isinstance(m.gate1, GatedSpatialConv2d)
+    bns = [x for x in m.modules() if isinstance(x, _BatchNorm)]
+    assert len(bns) == 150
+    assert sorted({b.momentum for b in bns}) == [0.001, 0.1]
+    assert sum(1 for b in bns if b.momentum == 0.001) == 6
+
+
+def test_library_exports_every_declared_symbol():
+    from saunet_b200 import _C
+    hdr = open(os.path.join(ROOT, "include", "saunet_b200.h")).read()
+    declared = set(re.findall(r"\b(saunet_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("saunet_conv_desc")
+    declared.discard("saunet_wgrad_desc")
+    assert declared == set(_C.ALL_SYMBOLS)
+    lib = ctypes.CDLL(_C.LIB_PATH)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert _C.load().saunet_version() >= 100
+
+
+def test_product_path_has_no_cpu_fallback():
+    from loss import DualLoss
+    m = _model()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        DualLoss()((torch.zeros(1, 4, 8, 8), torch.zeros(1, 1, 8, 8)), (torch.zeros(1, 8, 8), torch.zeros(1, 1, 8, 8)))
+    with pytest.raises(Exception, match="Architecture undefined"):
+        from models import ModelBuilder
+        ModelBuilder().build_unet(num_class=4, arch="albunet")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "shape-attentive-unet_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
