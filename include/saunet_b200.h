@@ -67,6 +67,10 @@ typedef struct saunet_conv_desc {
     int act;                     /* SAUNET_ACT_* */
     int accumulate;              /* y += result instead of y = result */
     double* stat_sum; double* stat_sumsq;
+    /* tensor-core path (conv_tc.cu): weights tiled by saunet_pack_weights_tc for N tile tc_bn; tc_passes 3 = 3xTF32
+     * (fp32-class accuracy), 1 = single-pass TF32.  NULL w_tc (or an ineligible geometry: Cin % 4 != 0, unaligned
+     * x) selects the exact-fp32 FFMA kernel, which reads `w`. */
+    const float* w_tc; int tc_bn; int tc_passes;
 } saunet_conv_desc;
 
 int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream);
@@ -81,6 +85,7 @@ typedef struct saunet_wgrad_desc {
     int KH, KW, Hg, Wg, sy, sx, offy, offx;
     const float* q_scale; const float* q_shift; int q_relu;
     float* dw;                   /* packed [KH*KW*Cb][Ca] */
+    int precision;               /* 0: exact fp32 FFMA;  1: tcgen05 3xTF32 (conv_wgrad_tc.cu) when the geometry allows */
 } saunet_wgrad_desc;
 int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream);
 
@@ -90,6 +95,13 @@ int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream);
  *  mode 2: packed[ph][(ty,tx,a)][b] = w[a][b][3-pa-2ty][3-pb-2tx], ph = pa*2+pb  (convT 4x4 s2 p1 fwd phases)
  * unpack: w_grad[a][b][t] (+)= packed[(t,b)][a]  (mode 0 only). */
 int saunet_pack_weights(const float* w, float* packed, int A, int Bc, int KH, int KW, int mode, void* stream);
+/* tensor-core weight tiling: kn = packed [K][N] (any mode above, one phase for mode 2) ->
+ * out[n_tile][k_block(32)][hi,lo][BN][32] in the UMMA K-major SWIZZLE_128B shared-memory image, tf32-split;
+ * K = taps*Cin, where Cin is the channel count of the tensor the conv GATHERS (so dgrad passes Cout). */
+int saunet_tc_tile_n(int Cout);
+long long saunet_tc_packed_floats(int K, int N, int BN, int passes);
+int saunet_tc_chunk_major(int taps, int Cin);   /* 1: K-blocks ordered (32-channel chunk, tap) for L1 reuse across taps */
+int saunet_pack_weights_tc(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream);
 int saunet_unpack_wgrad(const float* packed, float* wgrad, int A, int Bc, int KH, int KW, int accumulate, void* stream);
 
 /* ---- batch norm (nn.BatchNorm2d / SynchronizedBatchNorm2d outside DataParallel == F.batch_norm;

@@ -12,6 +12,10 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int conv_fwd_simt(const saunet_conv_desc* d, cudaStream_t st);
 int conv_wgrad_simt(const saunet_wgrad_desc* d, cudaStream_t st);
+int conv_fwd_tc(const saunet_conv_desc* d, cudaStream_t st);
+bool conv_tc_eligible(const saunet_conv_desc* d);
+int conv_wgrad_tc(const saunet_wgrad_desc* d, cudaStream_t st);
+bool conv_wgrad_tc_eligible(const saunet_wgrad_desc* d);
 }  // namespace saunet
 
 using namespace saunet;
@@ -31,6 +35,7 @@ extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
     SAUNET_CHECK_ARG((d->in_scale == nullptr) == (d->in_shift == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: in_scale/in_shift mismatch");
     SAUNET_CHECK_ARG((d->stat_sum == nullptr) == (d->stat_sumsq == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: stat_sum/stat_sumsq mismatch");
     SAUNET_CHECK_ARG(d->act >= 0 && d->act <= 2, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: bad activation %d", d->act);
+    if (conv_tc_eligible(d)) return conv_fwd_tc(d, (cudaStream_t)stream);
     return conv_fwd_simt(d, (cudaStream_t)stream);
 }
 
@@ -40,5 +45,6 @@ extern "C" int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream) {
                      d->Wg > 0 && d->sy > 0 && d->sx > 0, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: non-positive dimension");
     SAUNET_CHECK_ARG(d->p_ld >= d->Ca && d->q_ld >= d->Cb, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: ld smaller than channel count");
     SAUNET_CHECK_ARG((d->q_scale == nullptr) == (d->q_shift == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: q_scale/q_shift mismatch");
+    if (conv_wgrad_tc_eligible(d)) return conv_wgrad_tc(d, (cudaStream_t)stream);
     return conv_wgrad_simt(d, (cudaStream_t)stream);
 }

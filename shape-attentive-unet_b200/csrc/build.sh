@@ -9,7 +9,7 @@ mkdir -p "$HERE/_obj"
 pids=()
 for f in "$HERE"/*.cu; do
   o="$HERE/_obj/$(basename "${f%.cu}").o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/../../include/saunet_b200.h" -nt "$o" ]; then
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/tc_common.cuh" -nt "$o" ] || [ "$HERE/../../include/saunet_b200.h" -nt "$o" ]; then
     $NVCC $FLAGS -c "$f" -o "$o" &
     pids+=($!)
   fi

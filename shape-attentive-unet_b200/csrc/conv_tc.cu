@@ -1,0 +1,419 @@
+// conv_tc.cu -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators).
+//
+// GEMM view (same descriptor as conv_simt.cu): rows = 128 output pixels per CTA, N = Cout tile (16..256),
+// K = KH*KW*Cin in blocks of 32 fp32 (= one 128-byte swizzle row).
+//
+// Warp roles (192 threads, one output tile per CTA):
+//   warps 0-3  A producers: gather the im2col rows from NHWC global memory (128-bit loads), apply the fused
+//              BatchNorm+ReLU prologue, split every value into tf32 hi + lo, store both tiles into shared
+//              memory in the UMMA K-major SWIZZLE_128B layout, fence.proxy.async, arrive on full_a[stage].
+//              After the main loop the same warps run the epilogue (tcgen05.ld -> bias / BN-statistics /
+//              gate row-scale / activation -> global).
+//   warp 4     allocates TMEM; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8):
+//              3xTF32 = a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation in TMEM (error ~2^-21, the
+//              accuracy class the 1e-4 parity gate needs), or one pass (plain TF32) on request.
+//   warp 5     one lane streams the pre-tiled, pre-swizzled, pre-split weight tiles with cp.async.bulk (TMA
+//              engine, 1-D bulk copy) completing on full_b[stage].
+// Pipeline: NSTAGE-deep ring, mbarrier full/empty per stage, tcgen05.commit releases a stage.
+#include "tc_common.cuh"
+
+extern "C" int saunet_tc_chunk_major(int taps, int Cin);
+
+namespace saunet {
+
+struct TcP {
+    saunet_conv_desc d;
+    int M, K, HgWg, nkb;
+    int chunk_major;      // K ordered (32-channel chunk, tap, channel) instead of (tap, channel): see pack_tc_kernel
+    const float* wt;      // tiled weights: [n_tile][k_block][pass][BN][32] (swizzled image)
+};
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 128-byte rows, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// column sums of a [32 lanes][16 cols] register tile by transpose-reduce: 16 shuffles instead of 80.
+// afterwards lane L holds the sum of column (L >> 1).
+__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float send = (lane & 16) ? v[j] : v[j + 8], keep = (lane & 16) ? v[j + 8] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float send = (lane & 8) ? v[j] : v[j + 4], keep = (lane & 8) ? v[j + 4] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float send = (lane & 4) ? v[j] : v[j + 2], keep = (lane & 4) ? v[j + 2] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int BN, int NPASS>
+struct TcCfg {
+    static constexpr int A_BYTES = 128 * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int NOP = (NPASS == 3) ? 2 : 1;                 // hi (+ lo) images per operand
+    static constexpr int STAGE = NOP * (A_BYTES + B_BYTES);
+    static constexpr int NSTAGE_RAW = (192 * 1024) / STAGE;
+    static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : (NSTAGE_RAW < 2 ? 2 : NSTAGE_RAW);
+    static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    // The tensor core rounds its fp32 accumulator toward zero on every MMA, a bias that grows linearly with K
+    // (measured 4.5e-9*K normalised).  Round-robin the k-blocks over NACC TMEM accumulators and add them in the
+    // epilogue with round-to-nearest FADDs: the bias drops by ~NACC.
+    static constexpr int NACC = (512 / ACC_COLS) > 4 ? 4 : (512 / ACC_COLS);
+    static constexpr int TMEM_COLS = NACC * ACC_COLS;
+};
+
+constexpr int kProducers = 256;      // 8 producer / epilogue warps
+constexpr int kTcThreads = kProducers + 64;
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcP p) {
+    using Cfg = TcCfg<BN, NPASS>;
+    constexpr int NSTAGE = Cfg::NSTAGE;
+    constexpr int NACC = Cfg::NACC;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t bars = sbase + NSTAGE * Cfg::STAGE;
+    auto full_a = [&](int s) { return bars + 8u * s; };
+    auto full_b = [&](int s) { return bars + 8u * (NSTAGE + s); };
+    auto empty = [&](int s) { return bars + 8u * (2 * NSTAGE + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * NSTAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + NSTAGE * Cfg::STAGE + 8 * (3 * NSTAGE + 1));
+
+    const saunet_conv_desc& d = p.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
+    constexpr int MMA_WARP = kProducers / 32, LOAD_WARP = MMA_WARP + 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_a(s), kProducers); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < MMA_WARP) {
+        // ================= A producer =================
+        const int chunk = tid & 7, rbase = tid >> 3;          // 4 rows per thread: rbase + 32*i
+        int r_iy0[4], r_ix0[4], r_b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + rbase + 32 * i;
+            if (m < p.M) {
+                int b = m / p.HgWg; int r = m - b * p.HgWg; int gi = r / d.Wg; int gj = r - gi * d.Wg;
+                r_b[i] = b; r_iy0[i] = gi * d.sy + d.offy; r_ix0[i] = gj * d.sx + d.offx;
+            } else { r_b[i] = -1; r_iy0[i] = 0; r_ix0[i] = 0; }
+        }
+        const int taps = d.KH * d.KW;
+        // gather of one k-block into registers (padding tagged with a quiet NaN so it stays zero after the prologue)
+        auto load_block = [&](int kb, float4 (&v)[4], float4& sc, float4& sh) {
+            int c, tap; bool kval;
+            if (p.chunk_major) { const int cc = kb / taps; tap = kb - cc * taps; c = cc * 32 + chunk * 4; kval = true; }
+            else { const int k = kb * 32 + chunk * 4; kval = k < p.K; tap = kval ? k / d.Cin : 0; c = k - tap * d.Cin; }
+            const int ky = tap / d.KW, kx = tap - ky * d.KW;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int iy = r_iy0[i] + ky, ix = r_ix0[i] + kx;
+                const bool ok = kval && r_b[i] >= 0 && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win;
+                v[i] = make_float4(__int_as_float(0x7fc00001), 0.f, 0.f, 0.f);
+                if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(d.x + ((size_t)(r_b[i] * d.Hin + iy) * d.Win + ix) * d.x_ld + c));
+            }
+            sc = make_float4(1.f, 1.f, 1.f, 1.f); sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d.in_scale && kval) {
+                sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + c));
+                sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + c));
+            }
+        };
+        auto store_block = [&](int kb, const float4 (&v)[4], const float4& sc, const float4& sh) {
+            const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
+            mbar_wait(empty(s), ph ^ 1u);
+            uint8_t* a_hi = sgen + s * Cfg::STAGE;
+            uint8_t* a_lo = a_hi + Cfg::A_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 t = v[i];
+                if (__float_as_int(t.x) == 0x7fc00001) t = make_float4(0.f, 0.f, 0.f, 0.f);
+                else if (d.in_scale) {
+                    t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
+                    if (d.in_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+                }
+                const int r = rbase + 32 * i;
+                const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+                float4 hi = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
+                *reinterpret_cast<float4*>(a_hi + off) = hi;
+                if (NPASS == 3) {
+                    float4 lo = make_float4(tf32_hi(t.x - hi.x), tf32_hi(t.y - hi.y), tf32_hi(t.z - hi.z), tf32_hi(t.w - hi.w));
+                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full_a(s));
+        };
+        // software pipeline: the gather for k-block kb+1 is in flight while kb is transformed and stored
+        float4 va[4], vb[4], sca, sha, scb, shb;
+        load_block(0, va, sca, sha);
+        for (int kb = 0; kb < p.nkb; kb += 2) {
+            if (kb + 1 < p.nkb) load_block(kb + 1, vb, scb, shb);
+            store_block(kb, va, sca, sha);
+            if (kb + 1 < p.nkb) {
+                if (kb + 2 < p.nkb) load_block(kb + 2, va, sca, sha);
+                store_block(kb + 1, vb, scb, shb);
+            }
+        }
+        // ================= epilogue =================
+        mbar_wait(accum_bar, 0u);
+        tc_fence_after();
+        const int q = warp & 3, half = warp >> 2;             // TMEM lane quarter, column half
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        const bool mval = m < p.M;
+        size_t opix = 0;
+        if (mval) {
+            int b = m / p.HgWg; int rr = m - b * p.HgWg; int gi = rr / d.Wg; int gj = rr - gi * d.Wg;
+            opix = (size_t)(b * d.Hout + gi * d.osy + d.oy0) * d.Wout + (gj * d.osx + d.ox0);
+        }
+        float* yp = d.y + opix * d.y_ld;
+        const float rs = (d.row_scale && mval) ? (d.row_scale[m] + d.row_scale_add) : 1.f;
+        const bool vst = (d.Cout % 4 == 0) && (d.y_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15u) == 0);
+        float* red = reinterpret_cast<float*>(sgen);          // [4 quarters][2][BN] floats, stage memory is free now
+        const int nacc = p.nkb < NACC ? p.nkb : NACC;
+        for (int c0 = half * 16; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= d.Cout) break;                     // warp-uniform
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            for (int a = 1; a < nacc; ++a) {
+                float u[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + c0), u);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += u[j];
+            }
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                const float bj = (d.bias && n < d.Cout) ? __ldg(d.bias + n) : 0.f;
+                v[j] = (mval && n < d.Cout) ? v[j] + bj : 0.f;
+                o[j] = apply_act(v[j] * rs, d.act);
+            }
+            if (mval) {
+                if (vst) {
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int n = n0 + c0 + 4 * qq;
+                        if (n < d.Cout) {
+                            float4* dst = reinterpret_cast<float4*>(yp + n);
+                            float4 w4 = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
+                            if (d.accumulate) { float4 cur = *dst; w4.x += cur.x; w4.y += cur.y; w4.z += cur.z; w4.w += cur.w; }
+                            *dst = w4;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n0 + c0 + j;
+                        if (n < d.Cout) yp[n] = d.accumulate ? yp[n] + o[j] : o[j];
+                    }
+                }
+            }
+            if (d.stat_sum) {
+                float sq[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                const float s1 = colsum16(v, lane);
+                const float s2 = colsum16(sq, lane);
+                if ((lane & 1) == 0) {
+                    red[(q * 2 + 0) * BN + c0 + (lane >> 1)] = s1;
+                    red[(q * 2 + 1) * BN + c0 + (lane >> 1)] = s2;
+                }
+            }
+        }
+        if (d.stat_sum) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int i = tid; i < BN; i += kProducers) {
+                if (n0 + i < d.Cout) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) { s1 += red[(w * 2 + 0) * BN + i]; s2 += red[(w * 2 + 1) * BN + i]; }
+                    atomicAdd(d.stat_sum + n0 + i, (double)s1);
+                    atomicAdd(d.stat_sumsq + n0 + i, (double)s2);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == MMA_WARP) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
+                mbar_wait(full_a(s), ph);
+                mbar_wait(full_b(s), ph);
+                tc_fence_after();
+                const uint32_t a_hi = sbase + s * Cfg::STAGE;
+                const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+                const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES;
+                const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+                const uint32_t acc = tmem + (uint32_t)((kb % NACC) * Cfg::ACC_COLS);
+                const uint32_t fresh = (kb < NACC) ? 0u : 1u;          // first k-block of each accumulator overwrites
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const uint64_t dah = make_desc(a_hi + kk * 32), dbh = make_desc(b_hi + kk * 32);
+                    if (NPASS == 3) {
+                        const uint64_t dal = make_desc(a_lo + kk * 32), dbl = make_desc(b_lo + kk * 32);
+                        mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));       // small terms first
+                        mma_tf32(acc, dah, dbl, idesc, 1u);
+                        mma_tf32(acc, dah, dbh, idesc, 1u);
+                    } else {
+                        mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                    }
+                }
+                mma_commit(empty(s));
+            }
+            mma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else if (warp == LOAD_WARP) {
+        // ================= weight-tile loader =================
+        if (lane == 0) {
+            constexpr uint32_t BYTES = Cfg::NOP * Cfg::B_BYTES;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wt) + (size_t)blockIdx.y * p.nkb * BYTES;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
+                mbar_wait(empty(s), ph ^ 1u);
+                mbar_expect_tx(full_b(s), BYTES);
+                bulk_g2s(sbase + s * Cfg::STAGE + Cfg::NOP * Cfg::A_BYTES, src + (size_t)kb * BYTES, BYTES, full_b(s));
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ---- weight tiling: [K][N] row-major (the SIMT packing) -> [n_tile][k_block][pass][BN][32] swizzled image ----
+// K order of the tiled image: tap-major (k = tap*Cin + c, the SIMT order) or, when taps > 1 and Cin % 32 == 0,
+// chunk-major (k-block = cchunk*taps + tap): the 9 taps of a 3x3 conv over one 32-channel chunk become consecutive
+// k-blocks, so a CTA re-reads the same ~(tile+halo) x 128 B of activations 9 times in a row -- from L1.
+__global__ void pack_tc_kernel(const float* __restrict__ kn, int K, int N, int BN, int npass, int nkb, int taps, int Cin,
+                               int chunk_major, float* __restrict__ out) {
+    const int nop = npass == 3 ? 2 : 1;
+    const long long tile_f = (long long)BN * 32;                    // floats per image
+    const int ntile = (N + BN - 1) / BN;
+    const long long total = (long long)ntile * nkb * nop * tile_f;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long r = idx;
+        const int e = (int)(r % 4); r /= 4;           // element within the 16-byte chunk
+        const int pc = (int)(r % 8); r /= 8;          // physical chunk within the 128-byte row
+        const int row = (int)(r % BN); r /= BN;
+        const int op = (int)(r % nop); r /= nop;
+        const int kb = (int)(r % nkb); r /= nkb;
+        const int nt = (int)r;
+        const int lc = pc ^ (row & 7);                // logical chunk
+        int k = kb * 32 + lc * 4 + e;
+        if (chunk_major) { const int cc = kb / taps, tap = kb - cc * taps; k = tap * Cin + cc * 32 + lc * 4 + e; }
+        const int n = nt * BN + row;
+        float w = (k < K && n < N) ? kn[(size_t)k * N + n] : 0.f;
+        float hi = tf32_hi(w);
+        out[idx] = (op == 0) ? hi : tf32_hi(w - hi);
+    }
+}
+
+template <int BN, int NPASS>
+static int launch_tc(const TcP& p, cudaStream_t st) {
+    using Cfg = TcCfg<BN, NPASS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SAUNET_ERR_CUDA; }
+        attr_set = true;
+    }
+    dim3 grid(cdiv(p.M, 128), cdiv(p.d.Cout, BN));
+    conv_tc_kernel<BN, NPASS><<<grid, kTcThreads, Cfg::SMEM, st>>>(p);
+    SAUNET_CHECK_LAUNCH("conv_tc_kernel");
+    return SAUNET_OK;
+}
+
+bool conv_tc_eligible(const saunet_conv_desc* d) {
+    if (!d->w_tc || d->tc_bn <= 0) return false;
+    if (d->Cin % 4 || d->x_ld % 4 || !aligned16(d->x)) return false;
+    if (d->in_scale && (!aligned16(d->in_scale) || !aligned16(d->in_shift))) return false;
+    if (!aligned16(d->w_tc)) return false;
+    return true;
+}
+
+int conv_fwd_tc(const saunet_conv_desc* d, cudaStream_t st) {
+    TcP p; p.d = *d;
+    long long M = (long long)d->B * d->Hg * d->Wg;
+    SAUNET_CHECK_ARG(M > 0 && M < (1ll << 31), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd(tc): bad M=%lld", M);
+    p.M = (int)M; p.K = d->KH * d->KW * d->Cin; p.HgWg = d->Hg * d->Wg; p.nkb = (p.K + 31) / 32; p.wt = d->w_tc;
+    p.chunk_major = saunet_tc_chunk_major(d->KH * d->KW, d->Cin);
+    const bool three = d->tc_passes != 1;
+    switch (d->tc_bn) {
+        case 16: return three ? launch_tc<16, 3>(p, st) : launch_tc<16, 1>(p, st);
+        case 32: return three ? launch_tc<32, 3>(p, st) : launch_tc<32, 1>(p, st);
+        case 64: return three ? launch_tc<64, 3>(p, st) : launch_tc<64, 1>(p, st);
+        case 128: return three ? launch_tc<128, 3>(p, st) : launch_tc<128, 1>(p, st);
+        case 256: return three ? launch_tc<256, 3>(p, st) : launch_tc<256, 1>(p, st);
+    }
+    set_error("conv2d_fwd(tc): unsupported N tile %d", d->tc_bn);
+    return SAUNET_ERR_BAD_SHAPE;
+}
+
+}  // namespace saunet
+
+using namespace saunet;
+
+extern "C" int saunet_tc_chunk_major(int taps, int Cin) { return (taps > 1 && Cin % 32 == 0) ? 1 : 0; }
+extern "C" int saunet_tc_tile_n(int Cout) {
+    if (Cout <= 16) return 16;
+    if (Cout <= 32) return 32;
+    if (Cout <= 64) return 64;
+    if (Cout <= 128) return 128;
+    return 256;
+}
+extern "C" long long saunet_tc_packed_floats(int K, int N, int BN, int passes) {
+    if (K <= 0 || N <= 0 || BN <= 0) return 0;
+    const long long nkb = (K + 31) / 32, ntile = (N + BN - 1) / BN;
+    return ntile * nkb * (passes == 3 ? 2 : 1) * BN * 32;
+}
+extern "C" int saunet_pack_weights_tc(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream) {
+    const int K = taps * Cin;
+    SAUNET_CHECK_ARG(kn && out && taps > 0 && Cin > 0 && N > 0, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: bad args");
+    SAUNET_CHECK_ARG(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: bad N tile %d", BN);
+    SAUNET_CHECK_ARG(passes == 1 || passes == 3, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: passes must be 1 or 3");
+    const long long total = saunet_tc_packed_floats(K, N, BN, passes);
+    int blocks = (int)((total + 255) / 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kn, K, N, BN, passes, (K + 31) / 32, taps, Cin,
+                                                             saunet_tc_chunk_major(taps, Cin), out);
+    SAUNET_CHECK_LAUNCH("pack_tc_kernel");
+    return SAUNET_OK;
+}

@@ -1,0 +1,311 @@
+// conv_wgrad_tc.cu -- convolution weight gradient on tcgen05 tensor cores.
+//
+//   dw[(tap, cb)][ca] += sum_pixels  Q[gather(pixel, tap)][cb] * P[pixel][ca]
+//
+// is a GEMM whose reduction dimension is the PIXEL axis, so both operands are "MN-major" for the tensor core:
+// NHWC memory already has the channels of one pixel contiguous, and a 128-byte row of 32 channels of one pixel is
+// exactly one row of the UMMA MN-major SWIZZLE_128B atom (32 channels x 8 pixels).  No transposes anywhere.
+//
+// One CTA owns (tap, 128-channel tile of the M-side operand, BN-channel tile of the N-side operand) and a
+// contiguous range of pixels (split-K over the grid x axis); fp32 partial tiles are combined with atomics.
+// The host picks which of Q / P sits on the 128-row M side (`swap`), so that the wider operand fills M.
+//   warps 0-7  producers: 128-bit gathers (im2col shift + padding for Q, fused BN+ReLU prologue recompute),
+//              tf32 hi/lo split, MN-major swizzled stores, fence.proxy.async, arrive.   Then the epilogue.
+//   warp 8     TMEM alloc + single-lane tcgen05.mma.kind::tf32 issue (M=128, N=BN, K=8 pixels), 3xTF32.
+#include "tc_common.cuh"
+
+namespace saunet {
+
+struct WgTcP {
+    saunet_wgrad_desc d;
+    long long M;            // pixels of the output grid
+    int HgWg;
+    long long pix_per_split;
+    int swap;               // 0: M side = Q (cb), N side = P (ca);  1: M side = P (ca), N side = Q (cb)
+    int mtiles, ntiles;
+};
+
+// MN-major tf32 operands have exactly one legal shared-memory layout: SWIZZLE_128B_BASE32B (layout type 1).
+// Atom = 4 pixels (K) x 128 bytes (32 channels, MN); inside a row the four 32-byte granules are XOR-swizzled with
+// the row index (byte-address bits [5,7) ^= bits [7,9)).  LBO = distance between 32-channel atoms, SBO = distance
+// between 4-pixel atoms; one K=8 MMA spans two of them.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
+// byte offset of 16-byte chunk `ch` (4 channels) of pixel `px` inside a tile of `atoms_mn` 32-channel atoms
+__device__ __forceinline__ uint32_t mn_off(int px, int ch, int atoms_mn) {
+    const int pr = px & 3, cc = ch & 7;
+    return (uint32_t)(px >> 2) * (uint32_t)(atoms_mn * 512) + (uint32_t)(ch >> 3) * 512u + (uint32_t)pr * 128u +
+           (uint32_t)((((cc >> 1) ^ pr) << 5) | ((cc & 1) << 4));
+}
+
+template <int BN>
+struct WgCfg {
+    static constexpr int KB = 32;                                  // pixels per k-block
+    static constexpr int R_BYTES = KB * 128 * 4;                   // one image of the M-side tile (16 KB)
+    static constexpr int S_BYTES = KB * BN * 4;
+    static constexpr int STAGE = 2 * (R_BYTES + S_BYTES);          // hi + lo of both
+    static constexpr int NSTAGE_RAW = (192 * 1024) / STAGE;
+    static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
+    static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+    static constexpr int NACC = (512 / BN) > 4 ? 4 : (512 / BN);
+    static constexpr int TMEM_COLS = NACC * BN;
+};
+
+constexpr int kWgProducers = 256;
+constexpr int kWgThreads = kWgProducers + 32;
+
+// source operand description seen by the producers
+struct OpSrc {
+    const float* ptr; int ld; int C; int c0;      // channel tile start
+    int gather;                                   // 1: Q (shifted by the tap, zero outside the image), 0: P
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kWgThreads) conv_wgrad_tc_kernel(const __grid_constant__ WgTcP p) {
+    using Cfg = WgCfg<BN>;
+    constexpr int NSTAGE = Cfg::NSTAGE, NACC = Cfg::NACC;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t bars = sbase + NSTAGE * Cfg::STAGE;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * NSTAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + NSTAGE * Cfg::STAGE + 8 * (2 * NSTAGE + 1));
+
+    const saunet_wgrad_desc& d = p.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int MMA_WARP = kWgProducers / 32;
+
+    // tile decode
+    int t = blockIdx.y;
+    const int nt = t % p.ntiles; t /= p.ntiles;
+    const int mt = t % p.mtiles; const int tap = t / p.mtiles;
+    const int ky = tap / d.KW, kx = tap - ky * d.KW;
+    OpSrc R, S;
+    if (!p.swap) { R = {d.q, d.q_ld, d.Cb, mt * 128, 1}; S = {d.p, d.p_ld, d.Ca, nt * BN, 0}; }
+    else         { R = {d.p, d.p_ld, d.Ca, mt * 128, 0}; S = {d.q, d.q_ld, d.Cb, nt * BN, 1}; }
+
+    const long long mbeg = (long long)blockIdx.x * p.pix_per_split;
+    long long mend = mbeg + p.pix_per_split; if (mend > p.M) mend = p.M;
+    const int nkb = mend > mbeg ? (int)((mend - mbeg + Cfg::KB - 1) / Cfg::KB) : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), kWgProducers); mbar_init(empty(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < MMA_WARP) {
+        if (nkb > 0) {
+            // ---------------- producers ----------------
+            // M side: 32 chunks (128 channels) per pixel: chunk = tid & 31, pixels (tid >> 5) + 8*i, i < 4
+            // N side: BN/4 chunks per pixel
+            constexpr int SCH = BN / 4;                       // chunks per pixel on the N side
+            constexpr int SPIX = kWgProducers / SCH;          // pixels covered per pass
+            constexpr int SIT = Cfg::KB / SPIX;               // passes (>= 1)
+            const int rch = tid & 31, rp0 = tid >> 5;
+            const int sch = tid % SCH, sp0 = tid / SCH;
+            const int rc = R.c0 + rch * 4, sc_ = S.c0 + sch * 4;
+            const bool rcv = rc < R.C, scv = sc_ < S.C;
+            // prologue constants of the gathered operand (fixed channel chunk per thread)
+            float4 qsc = make_float4(1.f, 1.f, 1.f, 1.f), qsh = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                const int qc = p.swap ? sc_ : rc; const bool qv = p.swap ? scv : rcv;
+                if (d.q_scale && qv) {
+                    qsc = __ldg(reinterpret_cast<const float4*>(d.q_scale + qc));
+                    qsh = __ldg(reinterpret_cast<const float4*>(d.q_shift + qc));
+                }
+            }
+            auto fetch = [&](const OpSrc& o, long long m, int c, bool cvalid) -> float4 {
+                float4 v = make_float4(__int_as_float(0x7fc00001), 0.f, 0.f, 0.f);       // "stays zero"
+                if (!cvalid || m >= mend) return v;
+                if (o.gather) {
+                    const int bi = (int)(m / p.HgWg); const int r = (int)(m - (long long)bi * p.HgWg);
+                    const int gi = r / d.Wg, gj = r - gi * d.Wg;
+                    const int iy = gi * d.sy + ky + d.offy, ix = gj * d.sx + kx + d.offx;
+                    if (iy < 0 || iy >= d.Hq || ix < 0 || ix >= d.Wq) return v;
+                    return __ldg(reinterpret_cast<const float4*>(o.ptr + ((size_t)(bi * d.Hq + iy) * d.Wq + ix) * o.ld + c));
+                }
+                return __ldg(reinterpret_cast<const float4*>(o.ptr + (size_t)m * o.ld + c));
+            };
+            auto put = [&](uint8_t* hi_img, uint8_t* lo_img, uint32_t off, float4 v, bool gathered) {
+                if (__float_as_int(v.x) == 0x7fc00001) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                else if (gathered && d.q_scale) {
+                    v.x = fmaf(v.x, qsc.x, qsh.x); v.y = fmaf(v.y, qsc.y, qsh.y); v.z = fmaf(v.z, qsc.z, qsh.z); v.w = fmaf(v.w, qsc.w, qsh.w);
+                    if (d.q_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                }
+                float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                float4 lo = make_float4(tf32_hi(v.x - hi.x), tf32_hi(v.y - hi.y), tf32_hi(v.z - hi.z), tf32_hi(v.w - hi.w));
+                *reinterpret_cast<float4*>(hi_img + off) = hi;
+                *reinterpret_cast<float4*>(lo_img + off) = lo;
+            };
+            auto load_block = [&](int kb, float4 (&vr)[4], float4 (&vs)[SIT]) {
+                const long long mb = mbeg + (long long)kb * Cfg::KB;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vr[i] = fetch(R, mb + rp0 + 8 * i, rc, rcv);
+#pragma unroll
+                for (int i = 0; i < SIT; ++i) vs[i] = fetch(S, mb + sp0 + SPIX * i, sc_, scv);
+            };
+            auto store_block = [&](int kb, const float4 (&vr)[4], const float4 (&vs)[SIT]) {
+                const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
+                mbar_wait(empty(s), ph ^ 1u);
+                uint8_t* r_hi = sgen + s * Cfg::STAGE;
+                uint8_t* r_lo = r_hi + Cfg::R_BYTES;
+                uint8_t* s_hi = r_lo + Cfg::R_BYTES;
+                uint8_t* s_lo = s_hi + Cfg::S_BYTES;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int px = rp0 + 8 * i;
+                    put(r_hi, r_lo, mn_off(px, rch, 4), vr[i], R.gather != 0);
+                }
+#pragma unroll
+                for (int i = 0; i < SIT; ++i) {
+                    const int px = sp0 + SPIX * i;
+                    put(s_hi, s_lo, mn_off(px, sch, BN / 32), vs[i], S.gather != 0);
+                }
+                fence_proxy_async();
+                mbar_arrive(full(s));
+            };
+            float4 ra[4], rb[4], sa[SIT], sb[SIT];
+            load_block(0, ra, sa);
+            for (int kb = 0; kb < nkb; kb += 2) {
+                if (kb + 1 < nkb) load_block(kb + 1, rb, sb);
+                store_block(kb, ra, sa);
+                if (kb + 1 < nkb) {
+                    if (kb + 2 < nkb) load_block(kb + 2, ra, sa);
+                    store_block(kb + 1, rb, sb);
+                }
+            }
+            // ---------------- epilogue: TMEM -> fp32 atomics into dw ----------------
+            mbar_wait(accum_bar, 0u);
+            tc_fence_after();
+            const int q = warp & 3, half = warp >> 2;
+            const int row = q * 32 + lane;                   // M-side channel within the tile
+            const int mch = R.c0 + row;
+            const int nacc = nkb < NACC ? nkb : NACC;
+            for (int c0 = half * 16; c0 < BN; c0 += 32) {
+                if (S.c0 + c0 >= S.C) break;
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                for (int a = 1; a < nacc; ++a) {
+                    float u[16];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0), u);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += u[j];
+                }
+                if (mch < R.C) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int nch = S.c0 + c0 + j;
+                        if (nch < S.C) {
+                            const int cb = p.swap ? nch : mch, ca = p.swap ? mch : nch;
+                            atomicAdd(d.dw + ((size_t)tap * d.Cb + cb) * d.Ca + ca, v[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    } else {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0 && nkb > 0) {
+            // D=f32, A=B=tf32, both MN-major (bits 15, 16), N=BN, M=128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
+                mbar_wait(full(s), ph);
+                tc_fence_after();
+                const uint32_t r_hi = sbase + s * Cfg::STAGE;
+                const uint32_t r_lo = r_hi + Cfg::R_BYTES;
+                const uint32_t s_hi = r_lo + Cfg::R_BYTES;
+                const uint32_t s_lo = s_hi + Cfg::S_BYTES;
+                const uint32_t acc = tmem + (uint32_t)((kb % NACC) * BN);
+                const uint32_t fresh = (kb < NACC) ? 0u : 1u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {                 // 4 groups of 8 pixels
+                    const uint64_t drh = make_desc_mn(r_hi + j * 4096, 512, 2048), drl = make_desc_mn(r_lo + j * 4096, 512, 2048);
+                    const uint64_t dsh = make_desc_mn(s_hi + j * (BN * 32), 512, BN * 16), dsl = make_desc_mn(s_lo + j * (BN * 32), 512, BN * 16);
+                    mma_tf32(acc, drl, dsh, idesc, (j ? 1u : fresh));
+                    mma_tf32(acc, drh, dsl, idesc, 1u);
+                    mma_tf32(acc, drh, dsh, idesc, 1u);
+                }
+                mma_commit(empty(s));
+            }
+            mma_commit(accum_bar);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+template <int BN>
+static int launch_wg(const WgTcP& p, dim3 grid, cudaStream_t st) {
+    using Cfg = WgCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) { set_error("conv_wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SAUNET_ERR_CUDA; }
+        attr_set = true;
+    }
+    conv_wgrad_tc_kernel<BN><<<grid, kWgThreads, Cfg::SMEM, st>>>(p);
+    SAUNET_CHECK_LAUNCH("conv_wgrad_tc_kernel");
+    return SAUNET_OK;
+}
+
+bool conv_wgrad_tc_eligible(const saunet_wgrad_desc* d) {
+    if (d->precision != 1) return false;
+    if (d->Ca % 4 || d->Cb % 4 || d->p_ld % 4 || d->q_ld % 4 || !aligned16(d->p) || !aligned16(d->q)) return false;
+    if (d->q_scale && (!aligned16(d->q_scale) || !aligned16(d->q_shift))) return false;
+    if (d->Ca < 8 || d->Cb < 8) return false;
+    return true;
+}
+
+int conv_wgrad_tc(const saunet_wgrad_desc* d, cudaStream_t st) {
+    WgTcP p; p.d = *d;
+    p.M = (long long)d->B * d->Hg * d->Wg; p.HgWg = d->Hg * d->Wg;
+    SAUNET_CHECK_ARG(p.M > 0, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad(tc): empty problem");
+    // the wider operand goes on the 128-row M side
+    p.swap = (d->Ca > d->Cb) ? 1 : 0;
+    const int Cm = p.swap ? d->Ca : d->Cb, Cn = p.swap ? d->Cb : d->Ca;
+    const int BN = Cn <= 32 ? 32 : (Cn <= 64 ? 64 : 128);
+    p.mtiles = cdiv(Cm, 128); p.ntiles = cdiv(Cn, BN);
+    const int taps = d->KH * d->KW;
+    const long long tiles = (long long)taps * p.mtiles * p.ntiles;
+    SAUNET_CHECK_ARG(tiles <= 65535, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad(tc): too many tiles");
+    // split the pixel axis so that ~2 CTAs per SM exist; at least 256 pixels per split
+    long long splits = ((long long)kNumSMs * 2 + tiles - 1) / tiles;
+    long long maxs = (p.M + 255) / 256;
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+    long long pps = (p.M + splits - 1) / splits;
+    pps = (pps + 31) / 32 * 32;
+    splits = (p.M + pps - 1) / pps;
+    p.pix_per_split = pps;
+    dim3 grid((unsigned)splits, (unsigned)tiles);
+    if (BN == 32) return launch_wg<32>(p, grid, st);
+    if (BN == 64) return launch_wg<64>(p, grid, st);
+    return launch_wg<128>(p, grid, st);
+}
+
+}  // namespace saunet

@@ -21,7 +21,8 @@ class ConvDesc(Structure):
                 ("oy0", c_int), ("ox0", c_int),
                 ("in_scale", c_void_p), ("in_shift", c_void_p), ("in_relu", c_int),
                 ("bias", c_void_p), ("row_scale", c_void_p), ("row_scale_add", c_float),
-                ("act", c_int), ("accumulate", c_int), ("stat_sum", c_void_p), ("stat_sumsq", c_void_p)]
+                ("act", c_int), ("accumulate", c_int), ("stat_sum", c_void_p), ("stat_sumsq", c_void_p),
+                ("w_tc", c_void_p), ("tc_bn", c_int), ("tc_passes", c_int)]
 
 
 class WgradDesc(Structure):
@@ -29,7 +30,7 @@ class WgradDesc(Structure):
                 ("q", c_void_p), ("q_ld", c_int), ("Cb", c_int), ("B", c_int), ("Hq", c_int), ("Wq", c_int),
                 ("KH", c_int), ("KW", c_int), ("Hg", c_int), ("Wg", c_int), ("sy", c_int), ("sx", c_int),
                 ("offy", c_int), ("offx", c_int),
-                ("q_scale", c_void_p), ("q_shift", c_void_p), ("q_relu", c_int), ("dw", c_void_p)]
+                ("q_scale", c_void_p), ("q_shift", c_void_p), ("q_relu", c_int), ("dw", c_void_p), ("precision", c_int)]
 
 
 _P, _I, _L, _F, _D = c_void_p, c_int, c_longlong, c_float, c_double
@@ -40,6 +41,7 @@ SIGNATURES = {
     "saunet_conv2d_wgrad": [POINTER(WgradDesc), _P],
     "saunet_pack_weights": [_P, _P, _I, _I, _I, _I, _I, _P],
     "saunet_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "saunet_pack_weights_tc": [_P, _I, _I, _I, _I, _I, _P, _P],
     "saunet_channel_stats": [_P, _I, _I, _L, _P, _P, _P],
     "saunet_add_d2f": [_P, _P, _I, _P],
     "saunet_bn_finalize": [_P, _P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P],
@@ -70,6 +72,9 @@ _SPECIAL = {
     "saunet_last_error": ([], c_char_p),
     "saunet_launch_count": ([], c_longlong),
     "saunet_canny_workspace_bytes": ([_I, _I, _I], c_longlong),
+    "saunet_tc_tile_n": ([_I], c_int),
+    "saunet_tc_chunk_major": ([_I, _I], c_int),
+    "saunet_tc_packed_floats": ([_I, _I, _I, _I], c_longlong),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
 

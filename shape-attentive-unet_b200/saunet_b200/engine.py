@@ -12,6 +12,8 @@ and the autograd boundary -- never for arithmetic on the path.  There is no CPU
 fallback: a non-CUDA tensor or a missing library raises.
 """
 import ctypes
+import os
+import weakref
 
 import torch
 
@@ -177,15 +179,57 @@ def packed(tp, w, mode, A=None, Bc=None):
     """Packed GEMM layout of a conv / conv-transpose weight (see saunet_pack_weights)."""
     key = (id(w), mode)
     ent = _PACK.get(key)
-    if ent is not None and ent[0] == w._version and ent[1] == w.data_ptr() and ent[2].device == w.device:
+    if ent is not None and ent[3]() is w and ent[0] == w._version and ent[1] == w.data_ptr():
         return ent[2].data_ptr()
     if not w.is_contiguous():
         raise RuntimeError("saunet_b200: conv weights must be contiguous")
     a, b, kh, kw = w.shape
     out = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
     _C.call("saunet_pack_weights", w.data_ptr(), out.data_ptr(), a, b, kh, kw, mode, tp.stream)
-    _PACK[key] = (w._version, w.data_ptr(), out)
+    _PACK[key] = (w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)))
     return out.data_ptr()
+
+
+# ---------------------------------------------------------------------------
+# arithmetic class of the convolutions:
+#   "fp32"   exact fp32 FFMA implicit GEMM (conv_simt.cu)
+#   "3xtf32" tcgen05 tensor cores, hi/lo tf32 split of both operands, fp32 accumulate in TMEM (fp32-class accuracy)
+#   "tf32"   tcgen05, single pass (what cuDNN does by default for PyTorch convs); ~1e-3 relative error
+_PRECISION = os.environ.get("SAUNET_PRECISION", "fp32")
+
+
+def set_precision(name):
+    global _PRECISION
+    if name not in ("fp32", "3xtf32", "tf32"):
+        raise ValueError("precision must be fp32 | 3xtf32 | tf32")
+    _PRECISION = name
+
+
+def get_precision():
+    return _PRECISION
+
+
+def packed_tc(tp, w, mode, taps, Cin, N, phase=0):
+    """Tensor-core tiling of a packed [K][N] weight (see saunet_pack_weights_tc) -> (ptr, BN, passes) or None."""
+    if _PRECISION == "fp32":
+        return None
+    passes = 3 if _PRECISION == "3xtf32" else 1
+    lib = _C.load()
+    bn = lib.saunet_tc_tile_n(N)
+    key = (id(w), mode, phase, bn, passes)
+    ent = _PACK.get(key)
+    if ent is not None and ent[3]() is w and ent[0] == w._version and ent[1] == w.data_ptr():
+        return ent[2].data_ptr(), bn, passes
+    K = taps * Cin
+    kn = packed(tp, w, mode) + 4 * phase * K * N
+    out = torch.empty(lib.saunet_tc_packed_floats(K, N, bn, passes), dtype=torch.float32, device=w.device)
+    _C.call("saunet_pack_weights_tc", kn, taps, Cin, N, bn, passes, out.data_ptr(), tp.stream)
+    _PACK[key] = (w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)))
+    return out.data_ptr(), bn, passes
+
+
+def _tc_ok(x, Cout, K):
+    return _PRECISION != "fp32" and x.C % 4 == 0 and x.ld % 4 == 0 and x.ptr % 16 == 0 and Cout >= 8 and K >= 32
 
 
 def _p(t):
@@ -195,7 +239,7 @@ def _p(t):
 # ---------------------------------------------------------------------------
 # thin op wrappers
 def conv(tp, x, wptr, Cout, KH, KW, y, Hg, Wg, sy=1, sx=1, offy=0, offx=0, osy=1, osx=1, oy0=0, ox0=0,
-         pro=0, pro_relu=0, bias=0, row_scale=0, row_add=0.0, act=ACT_NONE, acc=0, stat=None):
+         pro=0, pro_relu=0, bias=0, row_scale=0, row_add=0.0, act=ACT_NONE, acc=0, stat=None, wtc=None):
     d = ConvDesc()
     d.x, d.x_ld, d.B, d.Hin, d.Win, d.Cin = x.ptr, x.ld, x.B, x.H, x.W, x.C
     d.w, d.Cout, d.KH, d.KW = wptr, Cout, KH, KW
@@ -212,6 +256,10 @@ def conv(tp, x, wptr, Cout, KH, KW, y, Hg, Wg, sy=1, sx=1, offy=0, offx=0, osy=1
         d.stat_sum, d.stat_sumsq = stat
     else:
         d.stat_sum, d.stat_sumsq = None, None
+    if wtc is not None:
+        d.w_tc, d.tc_bn, d.tc_passes = wtc
+    else:
+        d.w_tc, d.tc_bn, d.tc_passes = None, 0, 0
     M = x.B * Hg * Wg
     _C.call("saunet_conv2d_fwd", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * x.C * Cout,
             nbytes=4.0 * (x.npix * x.C + M * Cout + KH * KW * x.C * Cout))
@@ -227,6 +275,7 @@ def wgrad(tp, p, q, dwptr, KH, KW, Hg, Wg, sy=1, sx=1, offy=0, offx=0, pro=0, pr
     else:
         d.q_scale, d.q_shift, d.q_relu = None, None, 0
     d.dw = dwptr
+    d.precision = 0 if _PRECISION == "fp32" else 1
     M = q.B * Hg * Wg
     _C.call("saunet_conv2d_wgrad", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * p.C * q.C,
             nbytes=4.0 * M * (p.C + q.C))
@@ -326,9 +375,10 @@ def conv2d(tp, x, w, b, y=None, stride=1, pad=0, pro=None, pro_relu=0, act=ACT_N
     if y is None:
         y = tp.new(x.B, Ho, Wo, Cout)
     assert (y.H, y.W, y.C) == (Ho, Wo, Cout)
+    K = KH * KW * Cin
     conv(tp, x, packed(tp, w, 0), Cout, KH, KW, y, Ho, Wo, sy=stride, sx=stride, offy=-pad, offx=-pad,
          pro=pro.state if pro is not None else 0, pro_relu=pro_relu, bias=_p(b), row_scale=row_scale, row_add=row_add,
-         act=act, stat=stat)
+         act=act, stat=stat, wtc=packed_tc(tp, w, 0, KH * KW, Cin, Cout) if _tc_ok(x, Cout, K) else None)
     r = ConvRec()
     r.x, r.y, r.w, r.b, r.k, r.stride, r.pad, r.pro, r.pro_relu = x, y, w, b, (KH, KW), stride, pad, pro, pro_relu
     return y, r
@@ -349,8 +399,9 @@ def conv2d_bwd(tp, r, dy, dx=None, dx_acc=0, need_bias=True):
     if dx is not None:
         if r.stride != 1:
             raise RuntimeError("saunet_b200: data gradient of a strided conv is not on the SAUNet path")
+        Kd = KH * KW * Cout
         conv(tp, dy, packed(tp, w, 1), Cin, KH, KW, dx, x.H, x.W, offy=-(KH - 1 - r.pad), offx=-(KW - 1 - r.pad),
-             acc=dx_acc)
+             acc=dx_acc, wtc=packed_tc(tp, w, 1, KH * KW, Cout, Cin) if _tc_ok(dy, Cin, Kd) else None)
 
 
 # ---- ConvTranspose2d k4 s2 p1 (attention_blocks.py:179-183, models.py:211) as 4 output phases ----------
@@ -358,11 +409,13 @@ def convT4(tp, x, w, b, y, stat=None):
     Cin, Cout, KH, KW = w.shape
     assert (KH, KW) == (4, 4) and Cin == x.C and y.C == Cout and y.H == 2 * x.H and y.W == 2 * x.W
     wp = packed(tp, w, 2)
+    K = 4 * Cin
     for pa in range(2):
         for pb in range(2):
             ph = pa * 2 + pb
-            conv(tp, x, wp + 4 * ph * (4 * Cin * Cout), Cout, 2, 2, y, x.H, x.W, offy=pa - 1, offx=pb - 1, osy=2, osx=2,
-                 oy0=pa, ox0=pb, bias=_p(b), stat=stat)
+            conv(tp, x, wp + 4 * ph * (K * Cout), Cout, 2, 2, y, x.H, x.W, offy=pa - 1, offx=pb - 1, osy=2, osx=2,
+                 oy0=pa, ox0=pb, bias=_p(b), stat=stat,
+                 wtc=packed_tc(tp, w, 2, 4, Cin, Cout, phase=ph) if _tc_ok(x, Cout, K) else None)
 
 
 def convT4_bwd(tp, x, w, b, dy, dx, dx_acc):
@@ -374,7 +427,8 @@ def convT4_bwd(tp, x, w, b, dy, dx, dx_acc):
     if b is not None and b.requires_grad:
         bias_grad(tp, dy, b)
     if dx is not None:
-        conv(tp, dy, packed(tp, w, 0), Cin, 4, 4, dx, x.H, x.W, sy=2, sx=2, offy=-1, offx=-1, acc=dx_acc)
+        conv(tp, dy, packed(tp, w, 0), Cin, 4, 4, dx, x.H, x.W, sy=2, sx=2, offy=-1, offx=-1, acc=dx_acc,
+             wtc=packed_tc(tp, w, 0, 16, Cout, Cin) if _tc_ok(dy, Cin, 16 * Cout) else None)
 
 
 # ---- resampling / pooling ------------------------------------------------------------------------------
@@ -425,10 +479,9 @@ class _TapeFn(torch.autograd.Function):
     output grads, replays the tape and hands back input and parameter gradients."""
 
     @staticmethod
-    def forward(ctx, body, arena, n_in, *args):
+    def forward(ctx, body, arena, record, n_in, *args):
         ins, params = args[:n_in], args[n_in:]
         dev = ins[0].device
-        record = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or any(t.requires_grad for t in ins))
         tp = Tape(dev, record)
         tp.arena = arena
         in_bufs = [to_nhwc(tp, t.detach()) for t in ins]
@@ -436,7 +489,7 @@ class _TapeFn(torch.autograd.Function):
         if tp.bn_tracked:
             torch._foreach_add_(tp.bn_tracked, 1)
         ctx.tp, ctx.in_bufs, ctx.outs, ctx.params = tp, in_bufs, outs, params
-        ctx.in_need = [t.requires_grad for t in ins]
+        ctx.in_need = list(ctx.needs_input_grad[4:4 + n_in])
         res = tuple(o.nchw() for o in outs)
         if not record:
             ctx.tp = None
@@ -465,7 +518,7 @@ class _TapeFn(torch.autograd.Function):
             gin.append(g.nchw() if g is not None else None)
         gp = [tp.pgrads.get(p) if p.requires_grad else None for p in ctx.params]
         ctx.tp = ctx.in_bufs = ctx.outs = None
-        return (None, None, None) + tuple(gin) + tuple(gp)
+        return (None, None, None, None) + tuple(gin) + tuple(gp)
 
 
 def run(module, body, inputs):
@@ -478,4 +531,6 @@ def run(module, body, inputs):
     for t in inputs:
         if not t.is_cuda:
             raise RuntimeError("saunet_b200: input tensors must be CUDA tensors; there is no CPU fallback")
-    return _TapeFn.apply(body, getattr(module, "_saunet_grad_arena", None), len(inputs), *inputs, *params)
+    # (grad mode is off inside Function.forward, so decide here whether a backward tape is needed)
+    record = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or any(t.requires_grad for t in inputs))
+    return _TapeFn.apply(body, getattr(module, "_saunet_grad_arena", None), record, len(inputs), *inputs, *params)

@@ -1,0 +1,138 @@
+"""tcgen05 implicit-GEMM convolution (conv_tc.cu) against the exact-fp32 FFMA kernel (conv_simt.cu) through the
+C-ABI entry point saunet_conv2d_fwd, on every geometry class of the SAUNet path.  3xTF32 must agree with fp32 to
+2e-5 normalised (it carries ~21 mantissa bits); single-pass TF32 to 3e-3."""
+import pytest
+import torch
+
+from saunet_b200 import _C, engine
+from saunet_b200.engine import ACT_NONE, ACT_RELU, ACT_SIGMOID, Tape, conv, packed, packed_tc
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+CASES = [
+    # B, H, W, Cin, Cout, k, stride, pad, x_ld_extra, y_ld_extra, prologue, bias, stats, rowscale, act, acc
+    (2, 16, 16, 64, 128, 1, 1, 0, 0, 0, True, False, True, False, ACT_NONE, 0),      # dense 1x1 + BN prologue + stats
+    (2, 16, 16, 128, 32, 3, 1, 1, 0, 96, True, False, True, False, ACT_NONE, 0),     # dense 3x3 into a concat slice
+    (1, 20, 12, 64, 64, 3, 1, 1, 0, 0, False, False, True, False, ACT_NONE, 0),      # BasicBlock conv, ragged M
+    (2, 9, 7, 48, 40, 3, 1, 1, 16, 0, False, True, False, False, ACT_RELU, 0),       # odd sizes, Cout not pow2, x slice
+    (2, 8, 8, 256, 512, 3, 1, 1, 0, 0, False, True, True, False, ACT_NONE, 0),       # deep K, two N tiles
+    (1, 16, 16, 32, 32, 1, 1, 0, 4, 0, False, False, False, True, ACT_NONE, 0),      # GSConv gate row scale
+    (2, 12, 12, 16, 8, 1, 1, 0, 0, 0, False, True, False, False, ACT_SIGMOID, 0),    # K=16 < 32 padded k-block
+    (2, 16, 16, 32, 64, 3, 1, 1, 0, 0, False, False, False, False, ACT_NONE, 1),     # accumulate (dgrad into grads)
+    (1, 32, 32, 8, 16, 7, 2, 3, 0, 0, False, False, True, False, ACT_NONE, 0),       # 7x7 stride 2
+    (3, 6, 5, 1024, 256, 1, 1, 0, 0, 0, True, False, False, False, ACT_NONE, 0),     # transition-like, K=1024
+]
+
+
+@pytest.mark.parametrize("passes,tol", [(3, 2e-5), (1, 3e-3)])
+@pytest.mark.parametrize("case", CASES)
+def test_conv_tc_matches_fp32(case, passes, tol):
+    B, H, W, Cin, Cout, k, stride, pad, xe, ye, pro, bias, stats, rowscale, act, acc = case
+    g = torch.Generator(device="cpu").manual_seed(hash(case) & 0xFFFF)
+    tp = Tape(DEV, False)
+    x = tp.new(B, H, W, Cin, ld=Cin + xe)
+    x.s.t.copy_(torch.randn(x.s.t.numel(), generator=g).to(DEV))
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV)
+    w._version  # plain tensor: has a version counter
+    bvec = torch.randn(Cout, generator=g).to(DEV) if bias else None
+    state = torch.cat([0.5 + torch.rand(Cin, generator=g), 0.3 * torch.randn(Cin, generator=g)]).to(DEV) if pro else None
+    rs = torch.rand(B * Ho * Wo, generator=g).to(DEV) if rowscale else None
+    y0 = torch.randn(B * Ho * Wo * (Cout + ye), generator=g).to(DEV)
+    outs, sums = [], []
+    for use_tc in (False, True):
+        engine.set_precision("fp32" if not use_tc else ("3xtf32" if passes == 3 else "tf32"))
+        y = tp.new(B, Ho, Wo, Cout, ld=Cout + ye)
+        y.s.t.copy_(y0)
+        st = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
+        wtc = packed_tc(tp, w, 0, k * k, Cin, Cout) if use_tc else None
+        assert (wtc is not None) == use_tc
+        conv(tp, x, packed(tp, w, 0), Cout, k, k, y, Ho, Wo, sy=stride, sx=stride, offy=-pad, offx=-pad,
+             pro=state.data_ptr() if pro else 0, pro_relu=1 if pro else 0, bias=bvec.data_ptr() if bias else 0,
+             row_scale=rs.data_ptr() if rowscale else 0, row_add=1.0, act=act, acc=acc,
+             stat=(st.data_ptr(), st.data_ptr() + 8 * Cout) if stats else None, wtc=wtc)
+        torch.cuda.synchronize()
+        outs.append(y.s.t.clone())
+        sums.append(st.clone())
+    engine.set_precision("fp32")
+    print("case", case[:8], "passes", passes, "err", _rel(outs[1], outs[0]))
+    assert _rel(outs[1], outs[0]) < tol
+    if ye:      # channels outside the written slice are untouched
+        v0 = outs[1].view(-1, Cout + ye)[:, Cout:]
+        assert torch.equal(v0, y0.view(-1, Cout + ye)[:, Cout:])
+    if stats:
+        assert _rel(sums[1], sums[0]) < max(tol, 1e-5)
+
+
+def test_conv_tc_convT_phase_and_dgrad_shapes():
+    """ConvTranspose2d 4x4 s2 p1 forward (4 phases) and its stride-2 data gradient on the tensor-core path vs fp32."""
+    from saunet_b200.engine import convT4, convT4_bwd
+    g = torch.Generator().manual_seed(5)
+    tp = Tape(DEV, False)
+    Cin, Cout, B, H, W = 64, 32, 2, 6, 5
+    w = torch.nn.Parameter((torch.randn(Cin, Cout, 4, 4, generator=g) / (4 * Cin) ** 0.5).to(DEV), requires_grad=False)
+    b = torch.nn.Parameter(torch.randn(Cout, generator=g).to(DEV), requires_grad=False)
+    x = tp.new(B, H, W, Cin)
+    x.s.t.copy_(torch.randn(x.s.t.numel(), generator=g).to(DEV))
+    dy = tp.new(B, 2 * H, 2 * W, Cout)
+    dy.s.t.copy_(torch.randn(dy.s.t.numel(), generator=g).to(DEV))
+    res = {}
+    for prec in ("fp32", "3xtf32"):
+        engine.set_precision(prec)
+        y = tp.new(B, 2 * H, 2 * W, Cout)
+        convT4(tp, x, w, b, y)
+        dx = tp.new(B, H, W, Cin)
+        convT4_bwd(tp, x, w, b, dy, dx, 0)
+        torch.cuda.synchronize()
+        res[prec] = (y.s.t.clone(), dx.s.t.clone())
+    engine.set_precision("fp32")
+    ref = torch.nn.functional.conv_transpose2d(x.nchw().cpu().double(), w.detach().cpu().double(), b.detach().cpu().double(),
+                                               stride=2, padding=1)
+    assert _rel(res["fp32"][0].view(B, 2 * H, 2 * W, Cout).permute(0, 3, 1, 2).cpu(), ref) < 1e-5
+    assert _rel(res["3xtf32"][0], res["fp32"][0]) < 2e-5
+    assert _rel(res["3xtf32"][1], res["fp32"][1]) < 2e-5
+
+
+WG_CASES = [
+    # B, H, W, Ca(P), Cb(Q), k, stride(sy), off, q_prologue, p_ld_extra, q_ld_extra
+    (2, 16, 16, 32, 128, 3, 1, -1, True, 0, 0),       # dense conv2: Q wide (M side), P = 32
+    (2, 16, 16, 128, 64, 1, 1, 0, True, 0, 192),      # dense conv1: P wide -> swapped, Q is a slice of a concat buffer
+    (1, 20, 12, 64, 64, 3, 1, -1, False, 0, 0),       # BasicBlock, M side padded to 128
+    (2, 9, 7, 40, 48, 3, 1, -1, False, 8, 16),        # ragged everything
+    (2, 8, 8, 512, 256, 3, 1, -1, False, 0, 0),       # several M / N tiles
+    (3, 24, 24, 16, 8, 1, 1, 0, False, 0, 0),         # tiny channel counts
+    (2, 6, 5, 64, 32, 4, 2, -1, False, 0, 0),         # conv-transpose wgrad: P = x (low-res), Q = dY gathered at stride 2
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_wgrad_tc_matches_fp32(case):
+    from saunet_b200.engine import wgrad
+    B, H, W, Ca, Cb, k, stride, off, pro, pe, qe = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    tp = Tape(DEV, False)
+    # output grid = P's pixel grid (H x W); Q lives on the gathered grid
+    Hq, Wq = (H * stride, W * stride) if stride == 2 else (H, W)
+    P = tp.new(B, H, W, Ca, ld=Ca + pe)
+    P.s.t.copy_(torch.randn(P.s.t.numel(), generator=g).to(DEV))
+    Q = tp.new(B, Hq, Wq, Cb, ld=Cb + qe)
+    Q.s.t.copy_(torch.randn(Q.s.t.numel(), generator=g).to(DEV))
+    state = torch.cat([0.5 + torch.rand(Cb, generator=g), 0.3 * torch.randn(Cb, generator=g)]).to(DEV) if pro else None
+    res = []
+    for prec in ("fp32", "3xtf32"):
+        engine.set_precision(prec)
+        dw = torch.zeros(k * k * Cb * Ca, dtype=torch.float32, device=DEV)
+        wgrad(tp, P, Q, dw.data_ptr(), k, k, H, W, sy=stride, sx=stride, offy=off, offx=off,
+              pro=state.data_ptr() if pro else 0, pro_relu=1 if pro else 0)
+        torch.cuda.synchronize()
+        res.append(dw)
+    engine.set_precision("fp32")
+    err = _rel(res[1], res[0])
+    print("wgrad case", case, "err", err)
+    assert err < 2e-5
