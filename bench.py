@@ -177,7 +177,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         prof, _C.PROFILE = _C.PROFILE, None
         agg = {}
-        for name, a, b, fl, nb in prof:
+        for name, a, b, fl, nb, _tag in prof:
             t = a.elapsed_time(b)
             e = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
             e[0] += t; e[1] += 1; e[2] += fl; e[3] += nb

@@ -69,14 +69,17 @@ struct TcCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int NOP = (NPASS == 3) ? 2 : 1;                 // hi (+ lo) images per operand
     static constexpr int STAGE = NOP * (A_BYTES + B_BYTES);
+    // narrow tiles: 2 smem stages (the register ring hides the gather latency) so that two CTAs share an SM and one
+    // CTA's epilogue overlaps the other's main loop; wide tiles: as many stages as fit, one CTA per SM
     static constexpr int NSTAGE_RAW = (192 * 1024) / STAGE;
-    static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : (NSTAGE_RAW < 2 ? 2 : NSTAGE_RAW);
+    static constexpr int NSTAGE = (2 * STAGE <= 100 * 1024) ? 2 : (NSTAGE_RAW > 4 ? 4 : (NSTAGE_RAW < 2 ? 2 : NSTAGE_RAW));
+    static constexpr int MIN_CTAS = (2 * STAGE <= 100 * 1024) ? 2 : 1;
     static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     // The tensor core rounds its fp32 accumulator toward zero on every MMA, a bias that grows linearly with K
     // (measured 4.5e-9*K normalised).  Round-robin the k-blocks over NACC TMEM accumulators and add them in the
     // epilogue with round-to-nearest FADDs: the bias drops by ~NACC.
-    static constexpr int NACC = (512 / ACC_COLS) > 4 ? 4 : (512 / ACC_COLS);
+    static constexpr int NACC = ((512 / MIN_CTAS) / ACC_COLS) > 4 ? 4 : ((512 / MIN_CTAS) / ACC_COLS);
     static constexpr int TMEM_COLS = NACC * ACC_COLS;
 };
 
@@ -84,7 +87,7 @@ constexpr int kProducers = 256;      // 8 producer / epilogue warps
 constexpr int kTcThreads = kProducers + 64;
 
 template <int BN, int NPASS>
-__global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcP p) {
+__global__ void __launch_bounds__(kTcThreads, TcCfg<BN, NPASS>::MIN_CTAS) conv_tc_kernel(const __grid_constant__ TcP p) {
     using Cfg = TcCfg<BN, NPASS>;
     constexpr int NSTAGE = Cfg::NSTAGE;
     constexpr int NACC = Cfg::NACC;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     constexpr int MMA_WARP = kProducers / 32, LOAD_WARP = MMA_WARP + 1;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_a(s), kProducers); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_a(s), kProducers / 32); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -120,37 +123,41 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     if (warp < MMA_WARP) {
         // ================= A producer =================
         const int chunk = tid & 7, rbase = tid >> 3;          // 4 rows per thread: rbase + 32*i
-        int r_iy0[4], r_ix0[4], r_b[4];
+        // per-row constants: element offset of (b, iy0, ix0) and the tap-(0,0) coordinates; rows past M get
+        // coordinates that fail every bounds test.  32-bit element offsets (host guarantees the tensor fits).
+        int r_iy0[4], r_ix0[4], r_base[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int m = m0 + rbase + 32 * i;
             if (m < p.M) {
                 int b = m / p.HgWg; int r = m - b * p.HgWg; int gi = r / d.Wg; int gj = r - gi * d.Wg;
-                r_b[i] = b; r_iy0[i] = gi * d.sy + d.offy; r_ix0[i] = gj * d.sx + d.offx;
-            } else { r_b[i] = -1; r_iy0[i] = 0; r_ix0[i] = 0; }
+                r_iy0[i] = gi * d.sy + d.offy; r_ix0[i] = gj * d.sx + d.offx;
+                r_base[i] = ((b * d.Hin + r_iy0[i]) * d.Win + r_ix0[i]) * d.x_ld;
+            } else { r_iy0[i] = -(1 << 28); r_ix0[i] = -(1 << 28); r_base[i] = 0; }
         }
         const int taps = d.KH * d.KW;
         // gather of one k-block into registers (padding tagged with a quiet NaN so it stays zero after the prologue)
-        auto load_block = [&](int kb, float4 (&v)[4], float4& sc, float4& sh) {
+        auto load_block = [&](int kb, float4 (&v)[4], int& cch) {
             int c, tap; bool kval;
             if (p.chunk_major) { const int cc = kb / taps; tap = kb - cc * taps; c = cc * 32 + chunk * 4; kval = true; }
             else { const int k = kb * 32 + chunk * 4; kval = k < p.K; tap = kval ? k / d.Cin : 0; c = k - tap * d.Cin; }
             const int ky = tap / d.KW, kx = tap - ky * d.KW;
+            const int tapoff = (ky * d.Win + kx) * d.x_ld + c;
+            cch = kval ? c : -1;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int iy = r_iy0[i] + ky, ix = r_ix0[i] + kx;
-                const bool ok = kval && r_b[i] >= 0 && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win;
+                const bool ok = kval && (unsigned)(r_iy0[i] + ky) < (unsigned)d.Hin && (unsigned)(r_ix0[i] + kx) < (unsigned)d.Win;
                 v[i] = make_float4(__int_as_float(0x7fc00001), 0.f, 0.f, 0.f);
-                if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(d.x + ((size_t)(r_b[i] * d.Hin + iy) * d.Win + ix) * d.x_ld + c));
-            }
-            sc = make_float4(1.f, 1.f, 1.f, 1.f); sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (d.in_scale && kval) {
-                sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + c));
-                sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + c));
+                if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(d.x + (r_base[i] + tapoff)));
             }
         };
-        auto store_block = [&](int kb, const float4 (&v)[4], const float4& sc, const float4& sh) {
+        auto store_block = [&](int kb, const float4 (&v)[4], int cch) {
             const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d.in_scale && cch >= 0) {
+                sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + cch));
+                sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + cch));
+            }
             mbar_wait(empty(s), ph ^ 1u);
             uint8_t* a_hi = sgen + s * Cfg::STAGE;
             uint8_t* a_lo = a_hi + Cfg::A_BYTES;
@@ -171,18 +178,27 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     *reinterpret_cast<float4*>(a_lo + off) = lo;
                 }
             }
+            // every writer fences its own generic-proxy stores towards the async proxy, the warp converges, and ONE
+            // lane arrives (256 per-thread arrivals on one mbarrier serialise in shared memory)
             fence_proxy_async();
-            mbar_arrive(full_a(s));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(s));
         };
-        // software pipeline: the gather for k-block kb+1 is in flight while kb is transformed and stored
-        float4 va[4], vb[4], sca, sha, scb, shb;
-        load_block(0, va, sca, sha);
-        for (int kb = 0; kb < p.nkb; kb += 2) {
-            if (kb + 1 < p.nkb) load_block(kb + 1, vb, scb, shb);
-            store_block(kb, va, sca, sha);
+        // software pipeline: a 3-deep register ring keeps two k-blocks of gathers in flight while one is stored
+        float4 v0[4], v1[4], v2[4];
+        int cc0 = -1, cc1 = -1, cc2 = -1;
+        load_block(0, v0, cc0);
+        if (p.nkb > 1) load_block(1, v1, cc1);
+        for (int kb = 0; kb < p.nkb; kb += 3) {
+            if (kb + 2 < p.nkb) load_block(kb + 2, v2, cc2);
+            store_block(kb, v0, cc0);
             if (kb + 1 < p.nkb) {
-                if (kb + 2 < p.nkb) load_block(kb + 2, va, sca, sha);
-                store_block(kb + 1, vb, scb, shb);
+                if (kb + 3 < p.nkb) load_block(kb + 3, v0, cc0);
+                store_block(kb + 1, v1, cc1);
+            }
+            if (kb + 2 < p.nkb) {
+                if (kb + 4 < p.nkb) load_block(kb + 4, v1, cc1);
+                store_block(kb + 2, v2, cc2);
             }
         }
         // ================= epilogue =================
@@ -367,6 +383,7 @@ bool conv_tc_eligible(const saunet_conv_desc* d) {
     if (d->Cin % 4 || d->x_ld % 4 || !aligned16(d->x)) return false;
     if (d->in_scale && (!aligned16(d->in_scale) || !aligned16(d->in_shift))) return false;
     if (!aligned16(d->w_tc)) return false;
+    if ((long long)d->B * d->Hin * d->Win * d->x_ld >= (1ll << 31)) return false;      // 32-bit element offsets
     return true;
 }
 

@@ -52,9 +52,10 @@ struct WgCfg {
     static constexpr int S_BYTES = KB * BN * 4;
     static constexpr int STAGE = 2 * (R_BYTES + S_BYTES);          // hi + lo of both
     static constexpr int NSTAGE_RAW = (192 * 1024) / STAGE;
-    static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
+    static constexpr int MIN_CTAS = 1;       // (two CTAs/SM would cap registers at 113 and spill the 3-deep gather ring)
+    static constexpr int NSTAGE = MIN_CTAS == 2 ? 2 : (NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW);
     static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
-    static constexpr int NACC = (512 / BN) > 4 ? 4 : (512 / BN);
+    static constexpr int NACC = ((512 / MIN_CTAS) / BN) > 4 ? 4 : ((512 / MIN_CTAS) / BN);
     static constexpr int TMEM_COLS = NACC * BN;
 };
 
@@ -68,7 +69,7 @@ struct OpSrc {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kWgThreads) conv_wgrad_tc_kernel(const __grid_constant__ WgTcP p) {
+__global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc_kernel(const __grid_constant__ WgTcP p) {
     using Cfg = WgCfg<BN>;
     constexpr int NSTAGE = Cfg::NSTAGE, NACC = Cfg::NACC;
     extern __shared__ uint8_t smem_raw[];
@@ -84,21 +85,20 @@ __global__ void __launch_bounds__(kWgThreads) conv_wgrad_tc_kernel(const __grid_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int MMA_WARP = kWgProducers / 32;
 
-    // tile decode
-    int t = blockIdx.y;
-    const int nt = t % p.ntiles; t /= p.ntiles;
-    const int mt = t % p.mtiles; const int tap = t / p.mtiles;
-    const int ky = tap / d.KW, kx = tap - ky * d.KW;
+    // tile decode.  The gathered operand Q is addressed by kq = tap*Cb + cb (im2col column), so a 128-wide tile
+    // spans several taps when Cb is small and dY (P) is read once per tile, not once per tap.
+    const int nt = blockIdx.y % p.ntiles, mt = blockIdx.y / p.ntiles;
+    const int CQ = d.KH * d.KW * d.Cb;
     OpSrc R, S;
-    if (!p.swap) { R = {d.q, d.q_ld, d.Cb, mt * 128, 1}; S = {d.p, d.p_ld, d.Ca, nt * BN, 0}; }
-    else         { R = {d.p, d.p_ld, d.Ca, mt * 128, 0}; S = {d.q, d.q_ld, d.Cb, nt * BN, 1}; }
+    if (!p.swap) { R = {d.q, d.q_ld, CQ, mt * 128, 1}; S = {d.p, d.p_ld, d.Ca, nt * BN, 0}; }
+    else         { R = {d.p, d.p_ld, d.Ca, mt * 128, 0}; S = {d.q, d.q_ld, CQ, nt * BN, 1}; }
 
     const long long mbeg = (long long)blockIdx.x * p.pix_per_split;
     long long mend = mbeg + p.pix_per_split; if (mend > p.M) mend = p.M;
     const int nkb = mend > mbeg ? (int)((mend - mbeg + Cfg::KB - 1) / Cfg::KB) : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), kWgProducers); mbar_init(empty(s), 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), kWgProducers / 32); mbar_init(empty(s), 1); }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -114,35 +114,51 @@ __global__ void __launch_bounds__(kWgThreads) conv_wgrad_tc_kernel(const __grid_
     if (warp < MMA_WARP) {
         if (nkb > 0) {
             // ---------------- producers ----------------
-            // M side: 32 chunks (128 channels) per pixel: chunk = tid & 31, pixels (tid >> 5) + 8*i, i < 4
+            // M side: 32 chunks (128 columns) per pixel: chunk = tid & 31, pixels (tid >> 5) + 8*i, i < 4
             // N side: BN/4 chunks per pixel
             constexpr int SCH = BN / 4;                       // chunks per pixel on the N side
             constexpr int SPIX = kWgProducers / SCH;          // pixels covered per pass
             constexpr int SIT = Cfg::KB / SPIX;               // passes (>= 1)
             const int rch = tid & 31, rp0 = tid >> 5;
             const int sch = tid % SCH, sp0 = tid / SCH;
-            const int rc = R.c0 + rch * 4, sc_ = S.c0 + sch * 4;
-            const bool rcv = rc < R.C, scv = sc_ < S.C;
-            // prologue constants of the gathered operand (fixed channel chunk per thread)
+            const int rk = R.c0 + rch * 4, sk = S.c0 + sch * 4;          // logical column of this thread's chunk
+            const bool rcv = rk < R.C, scv = sk < S.C;
+            // the gathered side's column -> (tap, channel); fixed per thread
+            const int gk = p.swap ? sk : rk;
+            const bool gv = p.swap ? scv : rcv;
+            int gtap = 0, gc = 0;
+            if (gv) { gtap = gk / d.Cb; gc = gk - gtap * d.Cb; }
+            const int gky = gtap / d.KW, gkx = gtap - gky * d.KW;
+            const int rc = R.gather ? gc : rk, sc_ = S.gather ? gc : sk;   // channel offset inside the source pixel
             float4 qsc = make_float4(1.f, 1.f, 1.f, 1.f), qsh = make_float4(0.f, 0.f, 0.f, 0.f);
-            {
-                const int qc = p.swap ? sc_ : rc; const bool qv = p.swap ? scv : rcv;
-                if (d.q_scale && qv) {
-                    qsc = __ldg(reinterpret_cast<const float4*>(d.q_scale + qc));
-                    qsh = __ldg(reinterpret_cast<const float4*>(d.q_shift + qc));
-                }
+            if (d.q_scale && gv) {
+                qsc = __ldg(reinterpret_cast<const float4*>(d.q_scale + gc));
+                qsh = __ldg(reinterpret_cast<const float4*>(d.q_shift + gc));
             }
-            auto fetch = [&](const OpSrc& o, long long m, int c, bool cvalid) -> float4 {
+            // pixel -> (image, row, col) of the gathered operand, kept incrementally: k-blocks are visited in order and
+            // each slot advances by 32 pixels per block (no divisions in the loop)
+            struct Pix { int b, gi, gj; };
+            auto decode = [&](long long m) {
+                Pix x; x.b = (int)(m / p.HgWg); const int r = (int)(m - (long long)x.b * p.HgWg);
+                x.gi = r / d.Wg; x.gj = r - x.gi * d.Wg; return x;
+            };
+            auto advance = [&](Pix& x) {
+                x.gj += Cfg::KB;
+                while (x.gj >= d.Wg) { x.gj -= d.Wg; if (++x.gi == d.Hg) { x.gi = 0; ++x.b; } }
+            };
+            constexpr int GSL = 4 > SIT ? 4 : SIT;
+            Pix gpx[GSL];
+#pragma unroll
+            for (int i = 0; i < GSL; ++i) gpx[i] = decode(p.swap ? (mbeg + sp0 + SPIX * i) : (mbeg + rp0 + 8 * i));
+            auto fetch = [&](const OpSrc& o, long long m, const Pix& x, int c, bool cvalid) -> float4 {
                 float4 v = make_float4(__int_as_float(0x7fc00001), 0.f, 0.f, 0.f);       // "stays zero"
                 if (!cvalid || m >= mend) return v;
                 if (o.gather) {
-                    const int bi = (int)(m / p.HgWg); const int r = (int)(m - (long long)bi * p.HgWg);
-                    const int gi = r / d.Wg, gj = r - gi * d.Wg;
-                    const int iy = gi * d.sy + ky + d.offy, ix = gj * d.sx + kx + d.offx;
+                    const int iy = x.gi * d.sy + gky + d.offy, ix = x.gj * d.sx + gkx + d.offx;
                     if (iy < 0 || iy >= d.Hq || ix < 0 || ix >= d.Wq) return v;
-                    return __ldg(reinterpret_cast<const float4*>(o.ptr + ((size_t)(bi * d.Hq + iy) * d.Wq + ix) * o.ld + c));
+                    return __ldg(reinterpret_cast<const float4*>(o.ptr + (((x.b * d.Hq + iy) * d.Wq + ix) * o.ld + c)));
                 }
-                return __ldg(reinterpret_cast<const float4*>(o.ptr + (size_t)m * o.ld + c));
+                return __ldg(reinterpret_cast<const float4*>(o.ptr + ((int)m * o.ld + c)));
             };
             auto put = [&](uint8_t* hi_img, uint8_t* lo_img, uint32_t off, float4 v, bool gathered) {
                 if (__float_as_int(v.x) == 0x7fc00001) v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -156,13 +172,17 @@ __global__ void __launch_bounds__(kWgThreads) conv_wgrad_tc_kernel(const __grid_
                 *reinterpret_cast<float4*>(lo_img + off) = lo;
             };
             auto load_block = [&](int kb, float4 (&vr)[4], float4 (&vs)[SIT]) {
+                if (kb >= nkb) return;
                 const long long mb = mbeg + (long long)kb * Cfg::KB;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) vr[i] = fetch(R, mb + rp0 + 8 * i, rc, rcv);
+                for (int i = 0; i < 4; ++i) vr[i] = fetch(R, mb + rp0 + 8 * i, gpx[i], rc, rcv);
 #pragma unroll
-                for (int i = 0; i < SIT; ++i) vs[i] = fetch(S, mb + sp0 + SPIX * i, sc_, scv);
+                for (int i = 0; i < SIT; ++i) vs[i] = fetch(S, mb + sp0 + SPIX * i, gpx[i], sc_, scv);
+#pragma unroll
+                for (int i = 0; i < GSL; ++i) advance(gpx[i]);
             };
             auto store_block = [&](int kb, const float4 (&vr)[4], const float4 (&vs)[SIT]) {
+                if (kb >= nkb) return;
                 const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
                 mbar_wait(empty(s), ph ^ 1u);
                 uint8_t* r_hi = sgen + s * Cfg::STAGE;
@@ -170,34 +190,28 @@ __global__ void __launch_bounds__(kWgThreads) conv_wgrad_tc_kernel(const __grid_
                 uint8_t* s_hi = r_lo + Cfg::R_BYTES;
                 uint8_t* s_lo = s_hi + Cfg::S_BYTES;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int px = rp0 + 8 * i;
-                    put(r_hi, r_lo, mn_off(px, rch, 4), vr[i], R.gather != 0);
-                }
+                for (int i = 0; i < 4; ++i) put(r_hi, r_lo, mn_off(rp0 + 8 * i, rch, 4), vr[i], R.gather != 0);
 #pragma unroll
-                for (int i = 0; i < SIT; ++i) {
-                    const int px = sp0 + SPIX * i;
-                    put(s_hi, s_lo, mn_off(px, sch, BN / 32), vs[i], S.gather != 0);
-                }
+                for (int i = 0; i < SIT; ++i) put(s_hi, s_lo, mn_off(sp0 + SPIX * i, sch, BN / 32), vs[i], S.gather != 0);
                 fence_proxy_async();
-                mbar_arrive(full(s));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full(s));
             };
-            float4 ra[4], rb[4], sa[SIT], sb[SIT];
-            load_block(0, ra, sa);
-            for (int kb = 0; kb < nkb; kb += 2) {
-                if (kb + 1 < nkb) load_block(kb + 1, rb, sb);
-                store_block(kb, ra, sa);
-                if (kb + 1 < nkb) {
-                    if (kb + 2 < nkb) load_block(kb + 2, ra, sa);
-                    store_block(kb + 1, rb, sb);
-                }
+            // register ring, two k-blocks of gathers in flight while a third is transformed and stored
+            float4 r0[4], r1[4], r2[4], s0[SIT], s1[SIT], s2[SIT];
+            load_block(0, r0, s0);
+            load_block(1, r1, s1);
+            for (int kb = 0; kb < nkb; kb += 3) {
+                load_block(kb + 2, r2, s2); store_block(kb, r0, s0);
+                load_block(kb + 3, r0, s0); store_block(kb + 1, r1, s1);
+                load_block(kb + 4, r1, s1); store_block(kb + 2, r2, s2);
             }
             // ---------------- epilogue: TMEM -> fp32 atomics into dw ----------------
             mbar_wait(accum_bar, 0u);
             tc_fence_after();
             const int q = warp & 3, half = warp >> 2;
-            const int row = q * 32 + lane;                   // M-side channel within the tile
-            const int mch = R.c0 + row;
+            const int row = q * 32 + lane;                   // M-side column within the tile
+            const int mcol = R.c0 + row;
             const int nacc = nkb < NACC ? nkb : NACC;
             for (int c0 = half * 16; c0 < BN; c0 += 32) {
                 if (S.c0 + c0 >= S.C) break;
@@ -209,13 +223,13 @@ __global__ void __launch_bounds__(kWgThreads) conv_wgrad_tc_kernel(const __grid_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += u[j];
                 }
-                if (mch < R.C) {
+                if (mcol < R.C) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        const int nch = S.c0 + c0 + j;
-                        if (nch < S.C) {
-                            const int cb = p.swap ? nch : mch, ca = p.swap ? mch : nch;
-                            atomicAdd(d.dw + ((size_t)tap * d.Cb + cb) * d.Ca + ca, v[j]);
+                        const int ncol = S.c0 + c0 + j;
+                        if (ncol < S.C) {
+                            const int kq = p.swap ? ncol : mcol, ca = p.swap ? mcol : ncol;
+                            atomicAdd(d.dw + (size_t)kq * d.Ca + ca, v[j]);
                         }
                     }
                 }
@@ -278,6 +292,8 @@ bool conv_wgrad_tc_eligible(const saunet_wgrad_desc* d) {
     if (d->Ca % 4 || d->Cb % 4 || d->p_ld % 4 || d->q_ld % 4 || !aligned16(d->p) || !aligned16(d->q)) return false;
     if (d->q_scale && (!aligned16(d->q_scale) || !aligned16(d->q_shift))) return false;
     if (d->Ca < 8 || d->Cb < 8) return false;
+    const long long M = (long long)d->B * d->Hg * d->Wg;                       // 32-bit element offsets in the kernel
+    if (M * d->p_ld >= (1ll << 31) || (long long)d->B * d->Hq * d->Wq * d->q_ld >= (1ll << 31)) return false;
     return true;
 }
 
@@ -285,13 +301,13 @@ int conv_wgrad_tc(const saunet_wgrad_desc* d, cudaStream_t st) {
     WgTcP p; p.d = *d;
     p.M = (long long)d->B * d->Hg * d->Wg; p.HgWg = d->Hg * d->Wg;
     SAUNET_CHECK_ARG(p.M > 0, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad(tc): empty problem");
-    // the wider operand goes on the 128-row M side
-    p.swap = (d->Ca > d->Cb) ? 1 : 0;
-    const int Cm = p.swap ? d->Ca : d->Cb, Cn = p.swap ? d->Cb : d->Ca;
+    // the wider operand goes on the 128-row M side; the gathered operand's width is its im2col width taps*Cb
+    const int CQ = d->KH * d->KW * d->Cb;
+    p.swap = (d->Ca > CQ) ? 1 : 0;
+    const int Cm = p.swap ? d->Ca : CQ, Cn = p.swap ? CQ : d->Ca;
     const int BN = Cn <= 32 ? 32 : (Cn <= 64 ? 64 : 128);
     p.mtiles = cdiv(Cm, 128); p.ntiles = cdiv(Cn, BN);
-    const int taps = d->KH * d->KW;
-    const long long tiles = (long long)taps * p.mtiles * p.ntiles;
+    const long long tiles = (long long)p.mtiles * p.ntiles;
     SAUNET_CHECK_ARG(tiles <= 65535, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad(tc): too many tiles");
     // split the pixel axis so that ~2 CTAs per SM exist; at least 256 pixels per split
     long long splits = ((long long)kNumSMs * 2 + tiles - 1) / tiles;

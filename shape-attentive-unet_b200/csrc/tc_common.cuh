@@ -25,9 +25,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
         if (ok) return;
-        if (++spins == 1024) t0 = clock64();
-        // watchdog: a protocol bug must trap, not hang the device
-        if (spins > 1024 && (clock64() - t0) > 4000000000ll) __trap();
+        // watchdog: a protocol bug must trap, not hang the device (clock read only every 4096 failed probes)
+        if ((++spins & 4095) == 0) {
+            if (t0 == 0) t0 = clock64();
+            else if ((clock64() - t0) > 4000000000ll) __trap();
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -63,9 +65,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // round-to-nearest tf32 (low 13 mantissa bits zero afterwards): hi = rn(v), lo = rn(v - hi) keeps every dropped
 // term of the 3xTF32 product at <= 2^-22 relative and unbiased
 __device__ __forceinline__ float tf32_hi(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
+    // == cvt.rna.tf32.f32 for finite inputs, as two integer ops (the cvt pipe runs at quarter rate)
+    return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 
 

@@ -118,14 +118,14 @@ def check(rc, name="saunet"):
 PROFILE = None
 
 
-def call(name, *args, flops=0, nbytes=0):
+def call(name, *args, flops=0, nbytes=0, tag=""):
     if PROFILE is not None:
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(load(), name)(*args)
         e1.record()
-        PROFILE.append((name, e0, e1, flops, nbytes))
+        PROFILE.append((name, e0, e1, flops, nbytes, tag))
     else:
         rc = getattr(load(), name)(*args)
     if rc != 0:

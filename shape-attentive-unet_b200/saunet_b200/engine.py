@@ -262,7 +262,8 @@ def conv(tp, x, wptr, Cout, KH, KW, y, Hg, Wg, sy=1, sx=1, offy=0, offx=0, osy=1
         d.w_tc, d.tc_bn, d.tc_passes = None, 0, 0
     M = x.B * Hg * Wg
     _C.call("saunet_conv2d_fwd", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * x.C * Cout,
-            nbytes=4.0 * (x.npix * x.C + M * Cout + KH * KW * x.C * Cout))
+            nbytes=4.0 * (x.npix * x.C + M * Cout + KH * KW * x.C * Cout),
+            tag="M%d K%dx%dx%d N%d s%d%s%s" % (M, KH, KW, x.C, Cout, sy, " pro" if pro else "", " tc" if wtc else ""))
 
 
 def wgrad(tp, p, q, dwptr, KH, KW, Hg, Wg, sy=1, sx=1, offy=0, offx=0, pro=0, pro_relu=0):
@@ -278,7 +279,7 @@ def wgrad(tp, p, q, dwptr, KH, KW, Hg, Wg, sy=1, sx=1, offy=0, offx=0, pro=0, pr
     d.precision = 0 if _PRECISION == "fp32" else 1
     M = q.B * Hg * Wg
     _C.call("saunet_conv2d_wgrad", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * p.C * q.C,
-            nbytes=4.0 * M * (p.C + q.C))
+            nbytes=4.0 * M * (p.C + q.C), tag="M%d taps%d Ca%d Cb%d s%d" % (M, KH * KW, p.C, q.C, sy))
 
 
 def channel_stats(tp, x, sum_ptr, sumsq_ptr):

@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Micro-benchmark of one conv geometry through the C-ABI (for ncu captures):
+   python tools/bench_conv.py fwd|wgrad B H W Cin Cout k [iters]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "shape-attentive-unet_b200"))
+import torch
+from saunet_b200 import engine
+from saunet_b200.engine import Tape, conv, wgrad, packed, packed_tc
+
+kind = sys.argv[1]
+B, H, W, Cin, Cout, k = map(int, sys.argv[2:8])
+iters = int(sys.argv[8]) if len(sys.argv) > 8 else 5
+engine.set_precision(os.environ.get("SAUNET_PRECISION", "3xtf32"))
+dev = torch.device("cuda", 0)
+tp = Tape(dev, False)
+x = tp.new(B, H, W, Cin); x.s.t.normal_()
+y = tp.new(B, H, W, Cout); y.s.t.normal_()
+w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
+st = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
+dw = torch.zeros(k * k * Cin * Cout, device=dev)
+def run():
+    if kind == "fwd":
+        conv(tp, x, packed(tp, w, 0), Cout, k, k, y, H, W, offy=-(k // 2), offx=-(k // 2),
+             stat=(st.data_ptr(), st.data_ptr() + 8 * Cout), wtc=packed_tc(tp, w, 0, k * k, Cin, Cout))
+    else:
+        wgrad(tp, y, x, dw.data_ptr(), k, k, H, W, offy=-(k // 2), offx=-(k // 2))
+for _ in range(2): run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(iters): run()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / iters
+fl = 2.0 * B * H * W * k * k * Cin * Cout
+print("%s B%d %dx%d %d->%d k%d: %.3f ms  %.1f TFLOP/s" % (kind, B, H, W, Cin, Cout, k, ms, fl / ms / 1e9))
