@@ -195,7 +195,7 @@ def packed(tp, w, mode, A=None, Bc=None):
 #   "fp32"   exact fp32 FFMA implicit GEMM (conv_simt.cu)
 #   "3xtf32" tcgen05 tensor cores, hi/lo tf32 split of both operands, fp32 accumulate in TMEM (fp32-class accuracy)
 #   "tf32"   tcgen05, single pass (what cuDNN does by default for PyTorch convs); ~1e-3 relative error
-_PRECISION = os.environ.get("SAUNET_PRECISION", "fp32")
+_PRECISION = os.environ.get("SAUNET_PRECISION", "3xtf32")
 
 
 def set_precision(name):
@@ -349,15 +349,19 @@ def bn_backward(tp, bn, dy, x, out, act, dx, dx_acc, dres=None, dres_acc=0):
     materialised, else the mask is recomputed from x.  dx may alias dy."""
     C = bn.C
     red = tp.dzeros(2 * C)
+    nout = 1 if (out is not None and act == ACT_RELU) else 0
     _C.call("saunet_bn_bwd_reduce", dy.ptr, dy.ld, x.ptr, x.ld, out.ptr if out is not None else None,
-            out.ld if out is not None else 0, bn.state, C, dy.npix, act, red, tp.stream)
+            out.ld if out is not None else 0, bn.state, C, dy.npix, act, red, tp.stream,
+            nbytes=4.0 * C * dy.npix * (2 + nout), tag="C%d npix%d" % (C, dy.npix))
     mod = bn.mod
     has_affine = mod.weight is not None
     _C.call("saunet_bn_bwd_apply", dy.ptr, dy.ld, x.ptr, x.ld, out.ptr if out is not None else None,
             out.ld if out is not None else 0, bn.state, _p(mod.weight), red, C, dy.npix, act, 1 if bn.training else 0,
             dx.ptr if dx is not None else None, dx.ld if dx is not None else 0, dx_acc,
             dres.ptr if dres is not None else None, dres.ld if dres is not None else 0, dres_acc,
-            tp.pgrad(mod.weight) if has_affine else None, tp.pgrad(mod.bias) if has_affine else None, tp.stream)
+            tp.pgrad(mod.weight) if has_affine else None, tp.pgrad(mod.bias) if has_affine else None, tp.stream,
+            nbytes=4.0 * C * dy.npix * (2 + nout + (1 + dx_acc if dx is not None else 0) + (1 + dres_acc if dres is not None else 0)),
+            tag="C%d npix%d" % (C, dy.npix))
 
 
 # ---------------------------------------------------------------------------

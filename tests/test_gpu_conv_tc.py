@@ -9,6 +9,7 @@ from saunet_b200.engine import ACT_NONE, ACT_RELU, ACT_SIGMOID, Tape, conv, pack
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda", 0)
+DEFAULT_PRECISION = engine.get_precision()
 
 
 def _rel(a, b):
@@ -60,7 +61,7 @@ def test_conv_tc_matches_fp32(case, passes, tol):
         torch.cuda.synchronize()
         outs.append(y.s.t.clone())
         sums.append(st.clone())
-    engine.set_precision("fp32")
+    engine.set_precision(DEFAULT_PRECISION)
     print("case", case[:8], "passes", passes, "err", _rel(outs[1], outs[0]))
     assert _rel(outs[1], outs[0]) < tol
     if ye:      # channels outside the written slice are untouched
@@ -91,7 +92,7 @@ def test_conv_tc_convT_phase_and_dgrad_shapes():
         convT4_bwd(tp, x, w, b, dy, dx, 0)
         torch.cuda.synchronize()
         res[prec] = (y.s.t.clone(), dx.s.t.clone())
-    engine.set_precision("fp32")
+    engine.set_precision(DEFAULT_PRECISION)
     ref = torch.nn.functional.conv_transpose2d(x.nchw().cpu().double(), w.detach().cpu().double(), b.detach().cpu().double(),
                                                stride=2, padding=1)
     assert _rel(res["fp32"][0].view(B, 2 * H, 2 * W, Cout).permute(0, 3, 1, 2).cpu(), ref) < 1e-5
@@ -132,7 +133,7 @@ def test_wgrad_tc_matches_fp32(case):
               pro=state.data_ptr() if pro else 0, pro_relu=1 if pro else 0)
         torch.cuda.synchronize()
         res.append(dw)
-    engine.set_precision("fp32")
+    engine.set_precision(DEFAULT_PRECISION)
     err = _rel(res[1], res[0])
     print("wgrad case", case, "err", err)
     assert err < 2e-5

@@ -26,5 +26,10 @@ for name, a, b, fl, nb, tag in prof:
     e = agg.setdefault((name, tag), [0.0, 0, 0.0, 0.0]); e[0] += a.elapsed_time(b); e[1] += 1; e[2] += fl; e[3] += nb
 tot = sum(e[0] for e in agg.values())
 print("total %.2f ms over %d calls" % (tot, len(prof)))
-for (name, tag), e in sorted(agg.items(), key=lambda kv: -kv[1][0])[:45]:
+byname = collections.Counter()
+for (name, tag), e in agg.items():
+    byname[name] += e[0]
+print("  ".join("%s %.1f" % (k.replace("saunet_", ""), v) for k, v in byname.most_common(12)))
+FILTER = os.environ.get("PROFILE_FILTER", "")
+for (name, tag), e in [kv for kv in sorted(agg.items(), key=lambda kv: -kv[1][0]) if FILTER in kv[0][0]][:45]:
     print("%7.3f ms %4d x  %6.1f TF/s %7.1f GB/s  %-24s %s" % (e[0], e[1], e[2] / e[0] / 1e9 if e[0] else 0, e[3] / e[0] / 1e6 if e[0] else 0, name.replace("saunet_", ""), tag))
