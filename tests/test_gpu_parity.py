@@ -193,10 +193,12 @@ def test_saunet_forward_vs_reference(tag, batch, size, training, precision):
 _NOISE = {}
 
 
-def _grad_noise(batch, size):
+def _grad_noise(batch, size, eps=1e-7):
     """The reference algorithm's own fp32 gradient noise: oracle grads at the fixture weights vs at weights
-    perturbed by 1e-7 relative (about one ulp).  -> {param: (elementwise normalised error, norm error)}"""
-    key = (batch, size)
+    perturbed by `eps` relative (1e-7 = about one ulp).  -> {param: (elementwise normalised error, norm error)}.
+    The backward has genuine bifurcations (e.g. cw.weight's gradient jumps by 2 % under a 1e-6 perturbation when
+    one saturated-sigmoid BCE pixel flips), which is why a measured floor is used instead of a fixed tolerance."""
+    key = (batch, size, eps)
     if key not in _NOISE:
         from oracle import saunet_oracle as O
         torch.set_num_threads(max(1, (torch.get_num_threads())))
@@ -206,7 +208,7 @@ def _grad_noise(batch, size):
         out = {k: (0.0, 0.0) for k in r0["grads"]}
         for seed in (1, 2, 3):
             gen = torch.Generator().manual_seed(seed)
-            w2 = {k: (v * (1 + 1e-7 * torch.randn(v.shape, generator=gen))
+            w2 = {k: (v * (1 + eps * torch.randn(v.shape, generator=gen))
                       if v.is_floating_point() and v.dim() >= 1 and "running" not in k else v) for k, v in w.items()}
             r1 = O.train_step(w2, data["image"], data["seg"], data["edge"])
             for k, v in r0["grads"].items():
@@ -232,9 +234,9 @@ def test_saunet_train_step_vs_reference(tag, batch, size, precision):
     params = dict(m.named_parameters())
     names = [str(n) for n in g["grad_names"]]
     assert set(names) == {k for k, p in params.items() if p.grad is not None}
-    noise = _grad_noise(batch, size)
-    # 3xTF32 rounds every product at ~2^-21 (about 8 fp32 ulp): allow 30x the 1-ulp noise there, 10x for exact fp32
-    nf = 10.0 if precision == "fp32" else 30.0
+    # exact fp32: 10x the 1-ulp (1e-7) noise; 3xTF32 rounds every product at ~2^-21 (about 10 ulp): 10x the 1e-6 noise
+    noise = _grad_noise(batch, size, 1e-7 if precision == "fp32" else 1e-6)
+    nf = 10.0
     for k, ref in zip(names, g["grad_l2"]):
         got = float(params[k].grad.double().norm())
         if _is_zero_bias(k):
