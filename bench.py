@@ -124,11 +124,12 @@ def run_ours(args):
     hb = host_batch(B, rank)
     resident = {k: v.to(dev) for k, v in hb.items()}
 
-    def step(feed):
+    def step(feed, reduce=True):
         arena.zero()
         loss, acc = seg_mod({"image": feed["image"], "mask": (feed["seg"], feed["edge"])}, 0)
         loss.backward()
-        arena.all_reduce()
+        if reduce:
+            arena.all_reduce()
         return loss
 
     def step_e2e():
@@ -173,7 +174,7 @@ def run_ours(args):
     cpu_base = None
     if rank == 0:
         _C.PROFILE = []
-        step(resident)
+        step(resident, reduce=False)          # rank 0 only: no collective in this pass
         torch.cuda.synchronize()
         prof, _C.PROFILE = _C.PROFILE, None
         agg = {}

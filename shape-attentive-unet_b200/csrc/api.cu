@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include <atomic>
 #include <string.h>
+#include <stdlib.h>
 
 namespace saunet {
 static thread_local char g_err[512] = "";
@@ -14,6 +15,8 @@ int conv_fwd_simt(const saunet_conv_desc* d, cudaStream_t st);
 int conv_wgrad_simt(const saunet_wgrad_desc* d, cudaStream_t st);
 int conv_fwd_tc(const saunet_conv_desc* d, cudaStream_t st);
 bool conv_tc_eligible(const saunet_conv_desc* d);
+int conv_fwd_halo(const saunet_conv_desc* d, cudaStream_t st);
+bool conv_halo_eligible(const saunet_conv_desc* d);
 int conv_wgrad_tc(const saunet_wgrad_desc* d, cudaStream_t st);
 bool conv_wgrad_tc_eligible(const saunet_wgrad_desc* d);
 }  // namespace saunet
@@ -35,6 +38,7 @@ extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
     SAUNET_CHECK_ARG((d->in_scale == nullptr) == (d->in_shift == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: in_scale/in_shift mismatch");
     SAUNET_CHECK_ARG((d->stat_sum == nullptr) == (d->stat_sumsq == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: stat_sum/stat_sumsq mismatch");
     SAUNET_CHECK_ARG(d->act >= 0 && d->act <= 2, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: bad activation %d", d->act);
+    if (conv_halo_eligible(d) && !getenv("SAUNET_NO_HALO")) return conv_fwd_halo(d, (cudaStream_t)stream);
     if (conv_tc_eligible(d)) return conv_fwd_tc(d, (cudaStream_t)stream);
     return conv_fwd_simt(d, (cudaStream_t)stream);
 }

@@ -1,0 +1,330 @@
+// conv_halo.cu -- 3x3 / stride 1 / pad 1 convolution (forward and data-gradient) on tcgen05 with a shared-memory
+// HALO patch: every activation is gathered, BN+ReLU-transformed and tf32-split ONCE per 32-channel chunk and then
+// consumed by all 9 taps, instead of 9 times as in the generic implicit-GEMM kernel (conv_tc.cu), whose producers
+// are instruction-bound.
+//
+// CTA tile = 16 rows x 8 columns of one image (M = 128).  Patch = 18 x 10 halo pixels, stored as 128-byte rows
+// (32 channels) at a pitch of kPitch rows per image row, in the UMMA K-major SWIZZLE_128B pattern computed from
+// the ABSOLUTE row index.  The A descriptor of tap (ky,kx) simply starts (ky*kPitch + kx) rows into the patch: the
+// hardware applies the 128B swizzle on absolute shared-memory address bits [7,10) (verified on B200 with
+// tools/exp/umma_shift_test.cu: shifted starts work with base_offset = 0), and the 8-row groups of the M=128
+// operand are the 8-pixel tile rows, kPitch*128 bytes apart (= the descriptor's stride-byte-offset).
+//
+// Warps: 0-7 patch producers then epilogue, 8 MMA issuer (+TMEM alloc), 9 weight-tile loader (cp.async.bulk; same
+// chunk-major tiled weight image as conv_tc.cu).  Patch double-buffered; weight tiles in a ring.
+#include "tc_common.cuh"
+
+namespace saunet {
+
+struct HaloP {
+    saunet_conv_desc d;
+    int tiles_x, tiles_y, nchunk;
+    const float* wt;
+};
+
+constexpr int kPitch = 10;                         // patch rows per image row: stride-byte-offset 1280 (verified: any multiple of 128 works)
+constexpr int kPatchRows = 18 * kPitch;
+constexpr int kPatchBytes = (kPatchRows * 128 + 1023) / 1024 * 1024;   // one image (hi or lo); 1024-aligned so that
+                                                                       // 'row index & 7' IS the absolute-address swizzle phase
+constexpr int kHaloItems = 18 * 10 * 8;            // 16-byte chunks per patch
+constexpr int kHaloProducers = 256;
+constexpr int kHaloThreads = kHaloProducers + 64;
+constexpr int kHaloIters = (kHaloItems + kHaloProducers - 1) / kHaloProducers;   // 6
+
+// Occupancy plan: TWO CTAs per SM.  A tile has only Cin/32 (2..8) patch fills, so a single CTA never reaches a
+// steady state; with two resident CTAs one fills its patch / runs its epilogue while the other's MMAs run.  The
+// patch is therefore single-buffered (the register prefetch of the next chunk still overlaps the MMAs) and the
+// weight ring is sized so that two CTAs fit in 227 KB.
+template <int BN, int NPASS>
+struct HaloCfg {
+    static constexpr int NOP = (NPASS == 3) ? 2 : 1;
+    static constexpr int NBUF = 1;
+    static constexpr int PATCH = NOP * kPatchBytes;                  // one buffer
+    static constexpr int B_STAGE = NOP * BN * 128;
+    static constexpr int B_SPACE = 111 * 1024 - NBUF * PATCH;
+    static constexpr int NSTB_RAW = B_SPACE / B_STAGE;
+    static constexpr int NSTB = NSTB_RAW > 4 ? 4 : NSTB_RAW;
+    static constexpr int SMEM = NBUF * PATCH + NSTB * B_STAGE + 1024 + 256;
+    static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    static constexpr int NACC = (256 / ACC_COLS) > 4 ? 4 : (256 / ACC_COLS);
+    static constexpr int TMEM_COLS = NACC * ACC_COLS;
+    static_assert(NSTB >= 2, "weight ring needs two stages");
+};
+
+template <int BN, int NPASS>
+__global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid_constant__ HaloP p) {
+    using Cfg = HaloCfg<BN, NPASS>;
+    constexpr int NSTB = Cfg::NSTB, NACC = Cfg::NACC;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    const uint32_t b_base = sbase + Cfg::NBUF * Cfg::PATCH;
+    const uint32_t bars = b_base + NSTB * Cfg::B_STAGE;
+    auto patch_full = [&](int i) { return bars + 8u * i; };
+    auto patch_empty = [&](int i) { return bars + 8u * (2 + i); };
+    auto b_full = [&](int s) { return bars + 8u * (4 + s); };
+    auto b_empty = [&](int s) { return bars + 8u * (4 + NSTB + s); };
+    const uint32_t accum_bar = bars + 8u * (4 + 2 * NSTB);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + Cfg::NBUF * Cfg::PATCH + NSTB * Cfg::B_STAGE + 8 * (5 + 2 * NSTB));
+
+    const saunet_conv_desc& d = p.d;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int MMA_WARP = kHaloProducers / 32, LOAD_WARP = MMA_WARP + 1;
+    // tile decode
+    int t = blockIdx.x;
+    const int txi = t % p.tiles_x; t /= p.tiles_x;
+    const int tyi = t % p.tiles_y; const int b = t / p.tiles_y;
+    const int y0 = tyi * 16, x0 = txi * 8;
+    const int n0 = blockIdx.y * BN;
+    const int nkb = p.nchunk * 9;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(patch_full(i), kHaloProducers / 32); mbar_init(patch_empty(i), 1); }
+        for (int s = 0; s < NSTB; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < MMA_WARP) {
+        // ================= patch producers =================
+        const int chunk = tid & 7;
+        int g_off[kHaloIters];           // element offset of the halo pixel (channel 0), -1 = outside the image / no item
+        uint32_t s_off[kHaloIters];      // byte offset inside a patch image
+#pragma unroll
+        for (int i = 0; i < kHaloIters; ++i) {
+            const int it = tid + kHaloProducers * i;
+            const int pix = it >> 3;
+            const int py = pix / 10, px = pix - py * 10;
+            const int iy = y0 - 1 + py, ix = x0 - 1 + px;
+            const bool ok = it < kHaloItems && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win;
+            g_off[i] = ok ? ((b * d.Hin + iy) * d.Win + ix) * d.x_ld + chunk * 4 : -1;
+            const int pr = py * kPitch + px;
+            s_off[i] = (it < kHaloItems) ? ((uint32_t)pr * 128u + (uint32_t)((chunk ^ (pr & 7)) << 4)) : 0xFFFFFFFFu;
+        }
+        auto load_chunk = [&](int cc, float4 (&v)[kHaloIters]) {
+#pragma unroll
+            for (int i = 0; i < kHaloIters; ++i) {
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g_off[i] >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(d.x + (g_off[i] + cc * 32)));
+            }
+        };
+        auto store_chunk = [&](int cc, const float4 (&v)[kHaloIters]) {
+            const int buf = cc % Cfg::NBUF; const uint32_t ph = (cc / Cfg::NBUF) & 1;
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d.in_scale) {
+                sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + cc * 32 + chunk * 4));
+                sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + cc * 32 + chunk * 4));
+            }
+            mbar_wait(patch_empty(buf), ph ^ 1u);
+            uint8_t* hi_img = sgen + buf * Cfg::PATCH;
+            uint8_t* lo_img = hi_img + kPatchBytes;
+#pragma unroll
+            for (int i = 0; i < kHaloIters; ++i) {
+                if (s_off[i] == 0xFFFFFFFFu) continue;
+                float4 tv = v[i];
+                if (g_off[i] >= 0 && d.in_scale) {          // padding stays exactly zero: the prologue is applied BEFORE it
+                    tv.x = fmaf(tv.x, sc.x, sh.x); tv.y = fmaf(tv.y, sc.y, sh.y); tv.z = fmaf(tv.z, sc.z, sh.z); tv.w = fmaf(tv.w, sc.w, sh.w);
+                    if (d.in_relu) { tv.x = fmaxf(tv.x, 0.f); tv.y = fmaxf(tv.y, 0.f); tv.z = fmaxf(tv.z, 0.f); tv.w = fmaxf(tv.w, 0.f); }
+                }
+                float4 hi = make_float4(tf32_hi(tv.x), tf32_hi(tv.y), tf32_hi(tv.z), tf32_hi(tv.w));
+                *reinterpret_cast<float4*>(hi_img + s_off[i]) = hi;
+                if (NPASS == 3) {
+                    float4 lo = make_float4(tf32_hi(tv.x - hi.x), tf32_hi(tv.y - hi.y), tf32_hi(tv.z - hi.z), tf32_hi(tv.w - hi.w));
+                    *reinterpret_cast<float4*>(lo_img + s_off[i]) = lo;
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(patch_full(buf));
+        };
+        float4 va[kHaloIters], vb[kHaloIters];
+        load_chunk(0, va);
+        for (int cc = 0; cc < p.nchunk; cc += 2) {
+            if (cc + 1 < p.nchunk) load_chunk(cc + 1, vb);
+            store_chunk(cc, va);
+            if (cc + 1 < p.nchunk) {
+                if (cc + 2 < p.nchunk) load_chunk(cc + 2, va);
+                store_chunk(cc + 1, vb);
+            }
+        }
+        // ================= epilogue =================
+        mbar_wait(accum_bar, 0u);
+        tc_fence_after();
+        const int q = warp & 3, half = warp >> 2;
+        const int row = q * 32 + lane;
+        const int oy = y0 + (row >> 3), ox = x0 + (row & 7);
+        const size_t m = (size_t)(b * d.Hout + oy) * d.Wout + ox;
+        float* yp = d.y + m * d.y_ld;
+        const float rs = d.row_scale ? (d.row_scale[m] + d.row_scale_add) : 1.f;
+        const bool vst = (d.Cout % 4 == 0) && (d.y_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15u) == 0);
+        float* red = reinterpret_cast<float*>(sgen);          // [4 quarters][2][BN], patch memory is free now
+        const int nacc = nkb < NACC ? nkb : NACC;
+        for (int c0 = half * 16; c0 < BN; c0 += 32) {
+            if (n0 + c0 >= d.Cout) break;
+            float v[16];
+            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            for (int a = 1; a < nacc; ++a) {
+                float u[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + c0), u);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += u[j];
+            }
+            float o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int n = n0 + c0 + j;
+                const float bj = (d.bias && n < d.Cout) ? __ldg(d.bias + n) : 0.f;
+                v[j] = (n < d.Cout) ? v[j] + bj : 0.f;
+                o[j] = apply_act(v[j] * rs, d.act);
+            }
+            if (vst) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const int n = n0 + c0 + 4 * qq;
+                    if (n < d.Cout) {
+                        float4* dst = reinterpret_cast<float4*>(yp + n);
+                        float4 w4 = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
+                        if (d.accumulate) { float4 cur = *dst; w4.x += cur.x; w4.y += cur.y; w4.z += cur.z; w4.w += cur.w; }
+                        *dst = w4;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < d.Cout) yp[n] = d.accumulate ? yp[n] + o[j] : o[j];
+                }
+            }
+            if (d.stat_sum) {
+                float sq[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                const float s1 = colsum16(v, lane);
+                const float s2 = colsum16(sq, lane);
+                if ((lane & 1) == 0) {
+                    red[(q * 2 + 0) * BN + c0 + (lane >> 1)] = s1;
+                    red[(q * 2 + 1) * BN + c0 + (lane >> 1)] = s2;
+                }
+            }
+        }
+        if (d.stat_sum) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int i = tid; i < BN; i += kHaloProducers) {
+                if (n0 + i < d.Cout) {
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) { s1 += red[(w * 2 + 0) * BN + i]; s2 += red[(w * 2 + 1) * BN + i]; }
+                    atomicAdd(d.stat_sum + n0 + i, (double)s1);
+                    atomicAdd(d.stat_sumsq + n0 + i, (double)s2);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int kb = 0;
+            for (int cc = 0; cc < p.nchunk; ++cc) {
+                const int buf = cc % Cfg::NBUF; const uint32_t pph = (cc / Cfg::NBUF) & 1;
+                mbar_wait(patch_full(buf), pph);
+                const uint32_t a_hi0 = sbase + buf * Cfg::PATCH;
+                const uint32_t a_lo0 = a_hi0 + kPatchBytes;
+                for (int tap = 0; tap < 9; ++tap, ++kb) {
+                    const int s = kb % NSTB; const uint32_t ph = (kb / NSTB) & 1;
+                    mbar_wait(b_full(s), ph);
+                    tc_fence_after();
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const uint32_t shift = (uint32_t)(ky * kPitch + kx) * 128u;
+                    const uint32_t b_hi = b_base + s * Cfg::B_STAGE;
+                    const uint32_t b_lo = b_hi + BN * 128;
+                    const uint32_t acc = tmem + (uint32_t)((kb % NACC) * Cfg::ACC_COLS);
+                    const uint32_t fresh = (kb < NACC) ? 0u : 1u;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t dah = make_desc_sbo(a_hi0 + shift + kk * 32, kPitch * 128), dbh = make_desc(b_hi + kk * 32);
+                        if (NPASS == 3) {
+                            const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kPitch * 128), dbl = make_desc(b_lo + kk * 32);
+                            mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));
+                            mma_tf32(acc, dah, dbl, idesc, 1u);
+                            mma_tf32(acc, dah, dbh, idesc, 1u);
+                        } else {
+                            mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                        }
+                    }
+                    mma_commit(b_empty(s));
+                }
+                mma_commit(patch_empty(buf));
+            }
+            mma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else if (warp == LOAD_WARP) {
+        if (lane == 0) {
+            constexpr uint32_t BYTES = Cfg::B_STAGE;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wt) + (size_t)blockIdx.y * nkb * BYTES;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % NSTB; const uint32_t ph = (kb / NSTB) & 1;
+                mbar_wait(b_empty(s), ph ^ 1u);
+                mbar_expect_tx(b_full(s), BYTES);
+                bulk_g2s(b_base + s * Cfg::B_STAGE, src + (size_t)kb * BYTES, BYTES, b_full(s));
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+template <int BN, int NPASS>
+static int launch_halo(const HaloP& p, cudaStream_t st) {
+    using Cfg = HaloCfg<BN, NPASS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        if (e != cudaSuccess) { set_error("conv_halo: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SAUNET_ERR_CUDA; }
+        attr_set = true;
+    }
+    dim3 grid(p.d.B * p.tiles_y * p.tiles_x, cdiv(p.d.Cout, BN));
+    conv_halo_kernel<BN, NPASS><<<grid, kHaloThreads, Cfg::SMEM, st>>>(p);
+    SAUNET_CHECK_LAUNCH("conv_halo_kernel");
+    return SAUNET_OK;
+}
+
+bool conv_tc_eligible(const saunet_conv_desc* d);
+
+bool conv_halo_eligible(const saunet_conv_desc* d) {
+    if (!conv_tc_eligible(d)) return false;
+    if (d->KH != 3 || d->KW != 3 || d->sy != 1 || d->sx != 1 || d->offy != -1 || d->offx != -1) return false;
+    if (d->osy != 1 || d->osx != 1 || d->oy0 != 0 || d->ox0 != 0) return false;
+    if (d->Hg != d->Hin || d->Wg != d->Win || d->Hout != d->Hin || d->Wout != d->Win) return false;
+    if (d->Cin % 32 || d->Hin % 16 || d->Win % 8) return false;
+    if (d->tc_bn > 128) return false;           // patch + weight ring of a 256-wide tile would not leave room for 2 CTAs/SM
+    return true;
+}
+
+int conv_fwd_halo(const saunet_conv_desc* d, cudaStream_t st) {
+    HaloP p; p.d = *d;
+    p.tiles_x = d->Win / 8; p.tiles_y = d->Hin / 16; p.nchunk = d->Cin / 32; p.wt = d->w_tc;
+    const bool three = d->tc_passes != 1;
+    switch (d->tc_bn) {
+        case 16: return three ? launch_halo<16, 3>(p, st) : launch_halo<16, 1>(p, st);
+        case 32: return three ? launch_halo<32, 3>(p, st) : launch_halo<32, 1>(p, st);
+        case 64: return three ? launch_halo<64, 3>(p, st) : launch_halo<64, 1>(p, st);
+        case 128: return three ? launch_halo<128, 3>(p, st) : launch_halo<128, 1>(p, st);
+    }
+    set_error("conv2d_fwd(halo): unsupported N tile %d", d->tc_bn);
+    return SAUNET_ERR_BAD_SHAPE;
+}
+
+}  // namespace saunet

@@ -70,4 +70,50 @@ __device__ __forceinline__ float tf32_hi(float v) {
 }
 
 
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 128-byte rows, 8-row groups 1024 bytes apart
+// same layout with an explicit stride between 8-row groups (halo patches: one image row of the patch per group)
+__device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);          // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+// column sums of a [32 lanes][16 cols] register tile by transpose-reduce: 16 shuffles instead of 80.
+// afterwards lane L holds the sum of column (L >> 1).
+__device__ __forceinline__ float colsum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float send = (lane & 16) ? v[j] : v[j + 8], keep = (lane & 16) ? v[j + 8] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float send = (lane & 8) ? v[j] : v[j + 4], keep = (lane & 8) ? v[j + 4] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float send = (lane & 4) ? v[j] : v[j + 2], keep = (lane & 4) ? v[j + 2] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        float send = (lane & 2) ? v[0] : v[1], keep = (lane & 2) ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+
 }  // namespace saunet

@@ -185,10 +185,28 @@ class SAUNet(nn.Module):
         f = self.encoder.features
         B, H, W = xb.B, xb.H, xb.W
         # ---- encoder: conv0 + norm0 (no relu0 / pool0, :304-305) ----
+        # The 3-channel image is carried as a zero-padded 4-channel NHWC buffer (and conv0's weight as a zero-padded
+        # [64,4,7,7] copy) so the stem's forward and weight gradient run on the tensor-core kernels (Cin % 4 == 0).
         C0 = f.conv0.weight.shape[0]
         n0m = _check_bn(f.norm0)
         st0 = _stat(tp, n0m, C0)
-        t0, r0 = conv2d(tp, xb, f.conv0.weight, None, stride=2, pad=3, stat=st0)
+        w0 = f.conv0.weight
+        Cin0, KH0, KW0 = w0.shape[1], w0.shape[2], w0.shape[3]
+        pad_c = (-Cin0) % 4
+        if pad_c:
+            ent = getattr(self, "_conv0_padded", None)
+            if ent is None or ent[0] != w0._version or ent[1] != w0.data_ptr():
+                w0p = torch.zeros(C0, Cin0 + pad_c, KH0, KW0, dtype=w0.dtype, device=w0.device)
+                w0p[:, :Cin0].copy_(w0.detach())
+                ent = (w0._version, w0.data_ptr(), w0p)
+                self._conv0_padded = ent
+            w0p = ent[2]
+            xin = tp.new(B, H, W, Cin0 + pad_c)
+            xin.s.t.zero_()
+            _C.call("saunet_nchw_to_nhwc", x_nchw.data_ptr(), xin.ptr, xin.ld, B, Cin0, H * W, tp.stream)
+        else:
+            w0p, xin = w0, xb
+        t0, r0 = conv2d(tp, xin, w0p, None, stride=f.conv0.stride[0], pad=f.conv0.padding[0], stat=st0)
         bn0 = bn_finalize(tp, n0m, C0, st0, t0.npix)
         stages = [(f.denseblock1, f.transition1), (f.denseblock2, f.transition2), (f.denseblock3, f.transition3),
                   (f.denseblock4, None)]
@@ -203,7 +221,19 @@ class SAUNet(nn.Module):
                 return
             dt0 = tp.new(t0.B, t0.H, t0.W, C0)
             bn_backward(tp, bn0, g, t0, None, ACT_NONE, dt0, 0)
-            conv2d_bwd(tp, r0, dt0, None)
+            if not w0.requires_grad:
+                return
+            if not pad_c:
+                conv2d_bwd(tp, r0, dt0, None)
+                return
+            # weight gradient in the padded layout, then the real channels are added into conv0.weight's gradient
+            taps, Cp = KH0 * KW0, Cin0 + pad_c
+            dwp = torch.zeros(taps * Cp * C0, dtype=torch.float32, device=tp.device)
+            engine.wgrad(tp, dt0, xin, dwp.data_ptr(), KH0, KW0, dt0.H, dt0.W, sy=r0.stride, sx=r0.stride, offy=-r0.pad,
+                         offx=-r0.pad)
+            g4 = torch.empty(C0 * Cp * taps, dtype=torch.float32, device=tp.device)
+            _C.call("saunet_unpack_wgrad", dwp.data_ptr(), g4.data_ptr(), C0, Cp, KH0, KW0, 0, tp.stream)
+            _C.call("saunet_copy_slice", g4.data_ptr(), Cp * taps, tp.pgrad(w0), Cin0 * taps, Cin0 * taps, C0, 1, tp.stream)
         tp.on_backward(bwd_stem)
 
         feats = []

@@ -28,6 +28,11 @@ CASES = [
     (2, 16, 16, 32, 64, 3, 1, 1, 0, 0, False, False, False, False, ACT_NONE, 1),     # accumulate (dgrad into grads)
     (1, 32, 32, 8, 16, 7, 2, 3, 0, 0, False, False, True, False, ACT_NONE, 0),       # 7x7 stride 2
     (3, 6, 5, 1024, 256, 1, 1, 0, 0, 0, True, False, False, False, ACT_NONE, 0),     # transition-like, K=1024
+    # 3x3 / s1 / p1 with H % 16 == 0, W % 8 == 0, Cin % 32 == 0 -> the halo-patch kernel (conv_halo.cu)
+    (2, 32, 24, 64, 64, 3, 1, 1, 0, 0, False, True, True, False, ACT_RELU, 0),
+    (1, 16, 8, 32, 16, 3, 1, 1, 32, 16, True, False, True, False, ACT_NONE, 0),
+    (3, 16, 40, 96, 128, 3, 1, 1, 0, 0, True, True, False, False, ACT_NONE, 1),
+    (2, 48, 16, 160, 48, 3, 1, 1, 0, 0, False, False, True, False, ACT_SIGMOID, 0),
 ]
 
 
