@@ -59,7 +59,7 @@ struct WgCfg {
     static constexpr int TMEM_COLS = NACC * BN;
 };
 
-constexpr int kWgProducers = 256;
+constexpr int kWgProducers = 512;      // 16 producer warps: the transform is issue-latency bound, 4 warps/scheduler hide it
 constexpr int kWgThreads = kWgProducers + 32;
 
 // source operand description seen by the producers
@@ -114,15 +114,18 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
     if (warp < MMA_WARP) {
         if (nkb > 0) {
             // ---------------- producers ----------------
-            // M side: 32 chunks (128 columns) per pixel: chunk = tid & 31, pixels (tid >> 5) + 8*i, i < 4
-            // N side: BN/4 chunks per pixel
+            // M side: 32 chunks (128 columns) per pixel: chunk = tid & 31, pixels (tid >> 5) + RSTEP*i, i < RIT
+            // N side: BN/4 chunks per pixel; when the tile has fewer than 512 chunks only the first threads load it
+            constexpr int RSTEP = kWgProducers / 32, RIT = Cfg::KB / RSTEP;       // 16, 2
             constexpr int SCH = BN / 4;                       // chunks per pixel on the N side
-            constexpr int SPIX = kWgProducers / SCH;          // pixels covered per pass
+            constexpr int SPIX_RAW = kWgProducers / SCH;
+            constexpr int SPIX = SPIX_RAW > Cfg::KB ? Cfg::KB : SPIX_RAW;          // pixels covered per pass
             constexpr int SIT = Cfg::KB / SPIX;               // passes (>= 1)
+            const bool s_active = tid < SCH * SPIX;
             const int rch = tid & 31, rp0 = tid >> 5;
             const int sch = tid % SCH, sp0 = tid / SCH;
             const int rk = R.c0 + rch * 4, sk = S.c0 + sch * 4;          // logical column of this thread's chunk
-            const bool rcv = rk < R.C, scv = sk < S.C;
+            const bool rcv = rk < R.C, scv = s_active && sk < S.C;
             // the gathered side's column -> (tap, channel); fixed per thread
             const int gk = p.swap ? sk : rk;
             const bool gv = p.swap ? scv : rcv;
@@ -146,10 +149,10 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
                 x.gj += Cfg::KB;
                 while (x.gj >= d.Wg) { x.gj -= d.Wg; if (++x.gi == d.Hg) { x.gi = 0; ++x.b; } }
             };
-            constexpr int GSL = 4 > SIT ? 4 : SIT;
+            constexpr int GSL = RIT > SIT ? RIT : SIT;
             Pix gpx[GSL];
 #pragma unroll
-            for (int i = 0; i < GSL; ++i) gpx[i] = decode(p.swap ? (mbeg + sp0 + SPIX * i) : (mbeg + rp0 + 8 * i));
+            for (int i = 0; i < GSL; ++i) gpx[i] = decode(p.swap ? (mbeg + (s_active ? sp0 : 0) + SPIX * i) : (mbeg + rp0 + RSTEP * i));
             auto fetch = [&](const OpSrc& o, long long m, const Pix& x, int c, bool cvalid) -> float4 {
                 float4 v = make_float4(__int_as_float(0x7fc00001), 0.f, 0.f, 0.f);       // "stays zero"
                 if (!cvalid || m >= mend) return v;
@@ -171,17 +174,17 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
                 *reinterpret_cast<float4*>(hi_img + off) = hi;
                 *reinterpret_cast<float4*>(lo_img + off) = lo;
             };
-            auto load_block = [&](int kb, float4 (&vr)[4], float4 (&vs)[SIT]) {
+            auto load_block = [&](int kb, float4 (&vr)[RIT], float4 (&vs)[SIT]) {
                 if (kb >= nkb) return;
                 const long long mb = mbeg + (long long)kb * Cfg::KB;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) vr[i] = fetch(R, mb + rp0 + 8 * i, gpx[i], rc, rcv);
+                for (int i = 0; i < RIT; ++i) vr[i] = fetch(R, mb + rp0 + RSTEP * i, gpx[i], rc, rcv);
 #pragma unroll
                 for (int i = 0; i < SIT; ++i) vs[i] = fetch(S, mb + sp0 + SPIX * i, gpx[i], sc_, scv);
 #pragma unroll
                 for (int i = 0; i < GSL; ++i) advance(gpx[i]);
             };
-            auto store_block = [&](int kb, const float4 (&vr)[4], const float4 (&vs)[SIT]) {
+            auto store_block = [&](int kb, const float4 (&vr)[RIT], const float4 (&vs)[SIT]) {
                 if (kb >= nkb) return;
                 const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
                 mbar_wait(empty(s), ph ^ 1u);
@@ -190,15 +193,17 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
                 uint8_t* s_hi = r_lo + Cfg::R_BYTES;
                 uint8_t* s_lo = s_hi + Cfg::S_BYTES;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) put(r_hi, r_lo, mn_off(rp0 + 8 * i, rch, 4), vr[i], R.gather != 0);
+                for (int i = 0; i < RIT; ++i) put(r_hi, r_lo, mn_off(rp0 + RSTEP * i, rch, 4), vr[i], R.gather != 0);
+                if (s_active) {
 #pragma unroll
-                for (int i = 0; i < SIT; ++i) put(s_hi, s_lo, mn_off(sp0 + SPIX * i, sch, BN / 32), vs[i], S.gather != 0);
+                    for (int i = 0; i < SIT; ++i) put(s_hi, s_lo, mn_off(sp0 + SPIX * i, sch, BN / 32), vs[i], S.gather != 0);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full(s));
             };
             // register ring, two k-blocks of gathers in flight while a third is transformed and stored
-            float4 r0[4], r1[4], r2[4], s0[SIT], s1[SIT], s2[SIT];
+            float4 r0[RIT], r1[RIT], r2[RIT], s0[SIT], s1[SIT], s2[SIT];
             load_block(0, r0, s0);
             load_block(1, r1, s1);
             for (int kb = 0; kb < nkb; kb += 3) {
@@ -209,11 +214,11 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
             // ---------------- epilogue: TMEM -> fp32 atomics into dw ----------------
             mbar_wait(accum_bar, 0u);
             tc_fence_after();
-            const int q = warp & 3, half = warp >> 2;
+            const int q = warp & 3, cgrp = warp >> 2;        // TMEM lane quarter, column group (16 warps -> 4 groups)
             const int row = q * 32 + lane;                   // M-side column within the tile
             const int mcol = R.c0 + row;
             const int nacc = nkb < NACC ? nkb : NACC;
-            for (int c0 = half * 16; c0 < BN; c0 += 32) {
+            for (int c0 = cgrp * 16; c0 < BN; c0 += 64) {
                 if (S.c0 + c0 >= S.C) break;
                 float v[16];
                 tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);

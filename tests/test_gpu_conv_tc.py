@@ -142,3 +142,60 @@ def test_wgrad_tc_matches_fp32(case):
     err = _rel(res[1], res[0])
     print("wgrad case", case, "err", err)
     assert err < 2e-5
+
+
+SKINNY = [
+    # B, H, W, Cin, Cout, x_ld_extra, y_ld_extra, prologue, bias, stats, rowscale, act, acc
+    (2, 128, 128, 33, 33, 3, 0, True, True, False, False, ACT_RELU, 0),     # GSConv gate conv on a 36-wide cat buffer
+    (2, 128, 128, 33, 1, 3, 0, False, True, True, False, ACT_NONE, 0),      # gate head + BN statistics
+    (1, 256, 128, 8, 1, 0, 0, False, False, False, False, ACT_SIGMOID, 0),  # fuse
+    (1, 128, 128, 2, 1, 0, 0, False, False, False, False, ACT_SIGMOID, 0),  # cw
+    (1, 128, 128, 1, 32, 0, 32, False, True, True, False, ACT_NONE, 0),     # expand into a concat slice
+    (2, 128, 128, 32, 4, 0, 0, False, True, False, False, ACT_NONE, 0),     # final
+    (2, 128, 128, 4, 32, 0, 0, False, False, False, False, ACT_NONE, 1),    # final's data gradient, accumulating
+    (2, 128, 128, 16, 16, 1, 0, False, False, False, True, ACT_NONE, 0),    # gated conv with the row gate
+]
+
+
+@pytest.mark.parametrize("case", SKINNY)
+def test_skinny_conv_matches_reference(case):
+    """conv_skinny.cu (one thread per pixel) against a float64 matmul reference, forward and weight gradient."""
+    from saunet_b200.engine import wgrad
+    B, H, W, Cin, Cout, xe, ye, pro, bias, stats, rowscale, act, acc = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    tp = Tape(DEV, False)
+    n = B * H * W
+    x = tp.new(B, H, W, Cin, ld=Cin + xe)
+    x.s.t.copy_(torch.randn(x.s.t.numel(), generator=g).to(DEV))
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).to(DEV)
+    bvec = torch.randn(Cout, generator=g).to(DEV) if bias else None
+    state = torch.cat([0.5 + torch.rand(Cin, generator=g), 0.3 * torch.randn(Cin, generator=g)]).to(DEV) if pro else None
+    rs = torch.rand(n, generator=g).to(DEV) if rowscale else None
+    y = tp.new(B, H, W, Cout, ld=Cout + ye)
+    y0 = torch.randn(y.s.t.numel(), generator=g).to(DEV)
+    y.s.t.copy_(y0)
+    st = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
+    conv(tp, x, packed(tp, w, 0), Cout, 1, 1, y, H, W, pro=state.data_ptr() if pro else 0, pro_relu=1 if pro else 0,
+         bias=bvec.data_ptr() if bias else 0, row_scale=rs.data_ptr() if rowscale else 0, row_add=1.0, act=act, acc=acc,
+         stat=(st.data_ptr(), st.data_ptr() + 8 * Cout) if stats else None)
+    xa = x.s.t.view(n, Cin + xe)[:, :Cin].double()
+    if pro:
+        xa = torch.relu(xa * state[:Cin].double() + state[Cin:].double())
+    pre = xa @ w.view(Cout, Cin).double().t() + (bvec.double() if bias else 0)
+    o = pre * ((rs.double() + 1.0)[:, None] if rowscale else 1.0)
+    o = torch.relu(o) if act == ACT_RELU else (torch.sigmoid(o) if act == ACT_SIGMOID else o)
+    if acc:
+        o = o + y0.view(n, Cout + ye)[:, :Cout].double()
+    got = y.s.t.view(n, Cout + ye)
+    assert _rel(got[:, :Cout], o) < 2e-6
+    if ye:
+        assert torch.equal(got[:, Cout:], y0.view(n, Cout + ye)[:, Cout:])
+    if stats:
+        assert _rel(st[:Cout], pre.sum(0)) < 1e-5 and _rel(st[Cout:], (pre * pre).sum(0)) < 1e-5
+    # weight gradient with P = a random dY, Q = x (with the prologue)
+    P = tp.new(B, H, W, Cout)
+    P.s.t.copy_(torch.randn(P.s.t.numel(), generator=g).to(DEV))
+    dw = torch.zeros(Cin * Cout, device=DEV)
+    wgrad(tp, P, x, dw.data_ptr(), 1, 1, H, W, pro=state.data_ptr() if pro else 0, pro_relu=1 if pro else 0)
+    ref = xa.t() @ P.s.t.view(n, Cout).double()
+    assert _rel(dw.view(Cin, Cout), ref) < 1e-5

@@ -31,5 +31,5 @@ for (name, tag), e in agg.items():
     byname[name] += e[0]
 print("  ".join("%s %.1f" % (k.replace("saunet_", ""), v) for k, v in byname.most_common(12)))
 FILTER = os.environ.get("PROFILE_FILTER", "")
-for (name, tag), e in [kv for kv in sorted(agg.items(), key=lambda kv: -kv[1][0]) if FILTER in kv[0][0]][:45]:
+for (name, tag), e in [kv for kv in sorted(agg.items(), key=lambda kv: -kv[1][0]) if FILTER in kv[0][0]][:int(os.environ.get("PROFILE_TOP", "45"))]:
     print("%7.3f ms %4d x  %6.1f TF/s %7.1f GB/s  %-24s %s" % (e[0], e[1], e[2] / e[0] / 1e9 if e[0] else 0, e[3] / e[0] / 1e6 if e[0] else 0, name.replace("saunet_", ""), tag))
