@@ -15,44 +15,70 @@ struct SkP {
 };
 
 // ---- forward / data gradient: y[m][0:Cout) = act(rs[m] * (sum_c pro(x[m][c]) * W[c][n] + bias[n])) ----
+// 128 pixels per block iteration: the input rows are copied to shared memory with coalesced loads (one thread per
+// pixel reading its own 100+ byte row straight from global would touch 32 cache lines per instruction), each
+// thread then computes its pixel from a conflict-free (odd-stride) shared row, and the outputs go back through
+// the same buffer so the global stores are coalesced too.
+constexpr int kSkTile = 128;
+
 template <int CO>
-__global__ void __launch_bounds__(256) skinny_fwd_kernel(const SkP p) {
+__global__ void __launch_bounds__(kSkTile) skinny_fwd_kernel(const SkP p) {
     __shared__ __align__(16) float Ws[kSkMaxC * CO];
     __shared__ float bs[CO], scs[kSkMaxC], shs[kSkMaxC];
-    __shared__ float red[8][2 * CO];
+    __shared__ float tile[kSkTile * (kSkMaxC + 1)];
+    __shared__ float red[kSkTile / 32][2 * CO];
     const saunet_conv_desc& d = p.d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < d.Cin * CO; i += 256) {
+    const int Cin = d.Cin, Cout = d.Cout;
+    const int si = Cin | 1, so = Cout | 1;                    // odd row strides: no bank conflicts
+    for (int i = tid; i < Cin * CO; i += kSkTile) {
         const int c = i / CO, n = i - c * CO;
-        Ws[i] = n < d.Cout ? d.w[(size_t)c * d.Cout + n] : 0.f;
+        Ws[i] = n < Cout ? d.w[(size_t)c * Cout + n] : 0.f;
     }
-    for (int i = tid; i < CO; i += 256) bs[i] = (d.bias && i < d.Cout) ? d.bias[i] : 0.f;
-    for (int i = tid; i < d.Cin; i += 256) { scs[i] = d.in_scale ? d.in_scale[i] : 1.f; shs[i] = d.in_scale ? d.in_shift[i] : 0.f; }
-    __syncthreads();
+    for (int i = tid; i < CO; i += kSkTile) bs[i] = (d.bias && i < Cout) ? d.bias[i] : 0.f;
+    for (int i = tid; i < Cin; i += kSkTile) { scs[i] = d.in_scale ? d.in_scale[i] : 1.f; shs[i] = d.in_scale ? d.in_shift[i] : 0.f; }
     float ssum[CO], ssq[CO];
 #pragma unroll
     for (int n = 0; n < CO; ++n) { ssum[n] = 0.f; ssq[n] = 0.f; }
-    for (int m = blockIdx.x * 256 + tid; m < p.M; m += gridDim.x * 256) {
-        const float* xp = d.x + (size_t)m * d.x_ld;
+    for (int m0 = blockIdx.x * kSkTile; m0 < p.M; m0 += gridDim.x * kSkTile) {
+        const int npx = min(kSkTile, p.M - m0);
+        __syncthreads();
+        for (int i = tid; i < npx * Cin; i += kSkTile) {
+            const int px = i / Cin, c = i - px * Cin;
+            tile[px * si + c] = __ldg(d.x + (size_t)(m0 + px) * d.x_ld + c);
+        }
+        __syncthreads();
         float acc[CO];
 #pragma unroll
         for (int n = 0; n < CO; ++n) acc[n] = bs[n];
-        for (int c = 0; c < d.Cin; ++c) {
-            float xv = __ldg(xp + c);
-            if (d.in_scale) { xv = fmaf(xv, scs[c], shs[c]); if (d.in_relu) xv = fmaxf(xv, 0.f); }
-            const float* wr = Ws + c * CO;
+        const bool valid = tid < npx;
+        if (valid) {
+            const float* xr = tile + tid * si;
+            for (int c = 0; c < Cin; ++c) {
+                float xv = xr[c];
+                if (d.in_scale) { xv = fmaf(xv, scs[c], shs[c]); if (d.in_relu) xv = fmaxf(xv, 0.f); }
+                const float* wr = Ws + c * CO;
 #pragma unroll
-            for (int n = 0; n < CO; ++n) acc[n] = fmaf(xv, wr[n], acc[n]);
-        }
-        const float rs = d.row_scale ? (d.row_scale[m] + d.row_scale_add) : 1.f;
-        float* yp = d.y + (size_t)m * d.y_ld;
-#pragma unroll
-        for (int n = 0; n < CO; ++n) {
-            if (n < d.Cout) {
-                ssum[n] += acc[n]; ssq[n] = fmaf(acc[n], acc[n], ssq[n]);
-                const float o = apply_act(acc[n] * rs, d.act);
-                yp[n] = d.accumulate ? yp[n] + o : o;
+                for (int n = 0; n < CO; ++n) acc[n] = fmaf(xv, wr[n], acc[n]);
             }
+        }
+        __syncthreads();                                      // everyone is done reading the input tile
+        if (valid) {
+            const float rs = d.row_scale ? (d.row_scale[m0 + tid] + d.row_scale_add) : 1.f;
+#pragma unroll
+            for (int n = 0; n < CO; ++n) {
+                if (n < Cout) {
+                    ssum[n] += acc[n]; ssq[n] = fmaf(acc[n], acc[n], ssq[n]);
+                    tile[tid * so + n] = apply_act(acc[n] * rs, d.act);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < npx * Cout; i += kSkTile) {
+            const int px = i / Cout, n = i - px * Cout;
+            float* yp = d.y + (size_t)(m0 + px) * d.y_ld + n;
+            const float o = tile[px * so + n];
+            *yp = d.accumulate ? *yp + o : o;
         }
     }
     if (d.stat_sum) {
@@ -62,12 +88,12 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const SkP p) {
             if (lane == 0) { red[warp][n] = a; red[warp][CO + n] = b; }
         }
         __syncthreads();
-        for (int i = tid; i < 2 * CO; i += 256) {
+        for (int i = tid; i < 2 * CO; i += kSkTile) {
             const int n = i % CO;
-            if (n < d.Cout) {
+            if (n < Cout) {
                 float s = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) s += red[w][i];
+                for (int w = 0; w < kSkTile / 32; ++w) s += red[w][i];
                 atomicAdd((i < CO ? d.stat_sum : d.stat_sumsq) + n, (double)s);
             }
         }
@@ -76,10 +102,10 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const SkP p) {
 
 template <int CO>
 static int launch_sk(const SkP& p, cudaStream_t st) {
-    long long blocks = ((long long)p.M + 255) / 256;
+    long long blocks = ((long long)p.M + kSkTile - 1) / kSkTile;
     const long long cap = (long long)kNumSMs * 8;
     if (blocks > cap) blocks = cap;
-    skinny_fwd_kernel<CO><<<(int)blocks, 256, 0, st>>>(p);
+    skinny_fwd_kernel<CO><<<(int)blocks, kSkTile, 0, st>>>(p);
     SAUNET_CHECK_LAUNCH("skinny_fwd_kernel");
     return SAUNET_OK;
 }
@@ -124,22 +150,33 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const saunet_wgrad_de
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const long long mbeg = (long long)blockIdx.x * pix_per_block;
     long long mend = mbeg + pix_per_block; if (mend > M) mend = M;
-    for (long long m0 = mbeg; m0 < mend; m0 += kSkPix) {
-        __syncthreads();
-        for (int i = tid; i < kSkPix * kSkMaxC; i += 256) {
+    // each thread stages 10 elements of Q and of P per 64-pixel chunk; the next chunk's loads are in flight while
+    // the current chunk is multiplied
+    constexpr int NL = kSkPix * kSkMaxC / 256;               // 10
+    float qv[NL], pv[NL];
+    auto fetch = [&](long long m0) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const int i = tid + 256 * k;
             const int px = i / kSkMaxC, c = i - px * kSkMaxC;
             const long long m = m0 + px;
-            float q = 0.f, pv = 0.f;
-            if (m < mend) {
-                if (c < d.Cb) {
-                    q = __ldg(d.q + (size_t)m * d.q_ld + c);
-                    if (d.q_scale) { q = fmaf(q, d.q_scale[c], d.q_shift[c]); if (d.q_relu) q = fmaxf(q, 0.f); }
-                }
-                if (c < d.Ca) pv = __ldg(d.p + (size_t)m * d.p_ld + c);
-            }
-            Qs[px][c] = q; Ps[px][c] = pv;
+            qv[k] = (m < mend && c < d.Cb) ? __ldg(d.q + (size_t)m * d.q_ld + c) : 0.f;
+            pv[k] = (m < mend && c < d.Ca) ? __ldg(d.p + (size_t)m * d.p_ld + c) : 0.f;
+        }
+    };
+    if (mbeg < mend) fetch(mbeg);
+    for (long long m0 = mbeg; m0 < mend; m0 += kSkPix) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const int i = tid + 256 * k;
+            const int px = i / kSkMaxC, c = i - px * kSkMaxC;
+            float q = qv[k];
+            if (d.q_scale && c < d.Cb && m0 + px < mend) { q = fmaf(q, d.q_scale[c], d.q_shift[c]); if (d.q_relu) q = fmaxf(q, 0.f); }
+            Qs[px][c] = q; Ps[px][c] = pv[k];
         }
         __syncthreads();
+        if (m0 + kSkPix < mend) fetch(m0 + kSkPix);
         if (owner) {
 #pragma unroll 8
             for (int px = 0; px < kSkPix; ++px) {
