@@ -43,7 +43,8 @@ class SegmentationModuleBase(nn.Module):
             p = preds == i
             anb = torch.sum(v & p).float()
             j = anb / (torch.sum(v).float() + torch.sum(p).float() - anb + 1e-10)
-            jaccard.append(j if j <= 1 else 0)
+            # reference: `j if j <= 1 else 0` (a host branch = a device sync per class); same value, no sync
+            jaccard.append(torch.where(j <= 1, j, torch.zeros_like(j)))
         return acc, jaccard
 
     def jaccard(self, pred, label):

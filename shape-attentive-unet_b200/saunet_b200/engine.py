@@ -86,6 +86,7 @@ class Tape:
         self._keep = []
         self.bn_tracked = []
         self.arena = None
+        self.repacked = []      # pack-cache entries refreshed under FORCE_PACK by this tape (flag reset at the end)
 
     # ---- memory ---------------------------------------------------------
     def new(self, B, H, W, C, ld=None):
@@ -173,20 +174,27 @@ class Tape:
 # ---------------------------------------------------------------------------
 # weight packing cache: (id(param), mode) -> (version, data_ptr, packed tensor)
 _PACK = {}
+FORCE_PACK = False      # set while a CUDA graph is being captured: pack kernels must be part of the graph
 
 
 def packed(tp, w, mode, A=None, Bc=None):
     """Packed GEMM layout of a conv / conv-transpose weight (see saunet_pack_weights)."""
     key = (id(w), mode)
     ent = _PACK.get(key)
-    if ent is not None and ent[3]() is w and ent[0] == w._version and ent[1] == w.data_ptr():
+    if ent is not None and ent[3]() is w and ent[1] == w.data_ptr() and (ent[0] == w._version or FORCE_PACK):
+        if FORCE_PACK and not ent[4]:
+            # re-pack in place into the cached buffer (its address is what later launches of the graph read)
+            a, b, kh, kw = w.shape
+            _C.call("saunet_pack_weights", w.data_ptr(), ent[2].data_ptr(), a, b, kh, kw, mode, tp.stream)
+            ent[4] = True
+            tp.repacked.append(ent)
         return ent[2].data_ptr()
     if not w.is_contiguous():
         raise RuntimeError("saunet_b200: conv weights must be contiguous")
     a, b, kh, kw = w.shape
     out = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
     _C.call("saunet_pack_weights", w.data_ptr(), out.data_ptr(), a, b, kh, kw, mode, tp.stream)
-    _PACK[key] = (w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)))
+    _PACK[key] = [w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)), False]
     return out.data_ptr()
 
 
@@ -209,22 +217,32 @@ def get_precision():
     return _PRECISION
 
 
-def packed_tc(tp, w, mode, taps, Cin, N, phase=0):
-    """Tensor-core tiling of a packed [K][N] weight (see saunet_pack_weights_tc) -> (ptr, BN, passes) or None."""
+def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None):
+    """Tensor-core tiling of a packed [K][N] weight (see saunet_pack_weights_tc) -> (ptr, BN, passes) or None.
+    M (GEMM rows) lets small problems take a narrower N tile so that at least ~one CTA per SM exists."""
     if _PRECISION == "fp32":
         return None
     passes = 3 if _PRECISION == "3xtf32" else 1
     lib = _C.load()
     bn = lib.saunet_tc_tile_n(N)
+    if M is not None:
+        mt = (M + 127) // 128
+        while bn > 32 and mt * ((N + bn - 1) // bn) < 148:
+            bn //= 2
     key = (id(w), mode, phase, bn, passes)
     ent = _PACK.get(key)
-    if ent is not None and ent[3]() is w and ent[0] == w._version and ent[1] == w.data_ptr():
-        return ent[2].data_ptr(), bn, passes
     K = taps * Cin
+    if ent is not None and ent[3]() is w and ent[1] == w.data_ptr() and (ent[0] == w._version or FORCE_PACK):
+        if FORCE_PACK and not ent[4]:
+            kn = packed(tp, w, mode) + 4 * phase * K * N
+            _C.call("saunet_pack_weights_tc", kn, taps, Cin, N, bn, passes, ent[2].data_ptr(), tp.stream)
+            ent[4] = True
+            tp.repacked.append(ent)
+        return ent[2].data_ptr(), bn, passes
     kn = packed(tp, w, mode) + 4 * phase * K * N
     out = torch.empty(lib.saunet_tc_packed_floats(K, N, bn, passes), dtype=torch.float32, device=w.device)
     _C.call("saunet_pack_weights_tc", kn, taps, Cin, N, bn, passes, out.data_ptr(), tp.stream)
-    _PACK[key] = (w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)))
+    _PACK[key] = [w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)), False]
     return out.data_ptr(), bn, passes
 
 
@@ -383,7 +401,7 @@ def conv2d(tp, x, w, b, y=None, stride=1, pad=0, pro=None, pro_relu=0, act=ACT_N
     K = KH * KW * Cin
     conv(tp, x, packed(tp, w, 0), Cout, KH, KW, y, Ho, Wo, sy=stride, sx=stride, offy=-pad, offx=-pad,
          pro=pro.state if pro is not None else 0, pro_relu=pro_relu, bias=_p(b), row_scale=row_scale, row_add=row_add,
-         act=act, stat=stat, wtc=packed_tc(tp, w, 0, KH * KW, Cin, Cout) if _tc_ok(x, Cout, K) else None)
+         act=act, stat=stat, wtc=packed_tc(tp, w, 0, KH * KW, Cin, Cout, M=x.B * Ho * Wo) if _tc_ok(x, Cout, K) else None)
     r = ConvRec()
     r.x, r.y, r.w, r.b, r.k, r.stride, r.pad, r.pro, r.pro_relu = x, y, w, b, (KH, KW), stride, pad, pro, pro_relu
     return y, r
@@ -406,7 +424,7 @@ def conv2d_bwd(tp, r, dy, dx=None, dx_acc=0, need_bias=True):
             raise RuntimeError("saunet_b200: data gradient of a strided conv is not on the SAUNet path")
         Kd = KH * KW * Cout
         conv(tp, dy, packed(tp, w, 1), Cin, KH, KW, dx, x.H, x.W, offy=-(KH - 1 - r.pad), offx=-(KW - 1 - r.pad),
-             acc=dx_acc, wtc=packed_tc(tp, w, 1, KH * KW, Cout, Cin) if _tc_ok(dy, Cin, Kd) else None)
+             acc=dx_acc, wtc=packed_tc(tp, w, 1, KH * KW, Cout, Cin, M=x.npix) if _tc_ok(dy, Cin, Kd) else None)
 
 
 # ---- ConvTranspose2d k4 s2 p1 (attention_blocks.py:179-183, models.py:211) as 4 output phases ----------
@@ -497,6 +515,8 @@ class _TapeFn(torch.autograd.Function):
         ctx.in_need = list(ctx.needs_input_grad[4:4 + n_in])
         res = tuple(o.nchw() for o in outs)
         if not record:
+            for ent in tp.repacked:
+                ent[4] = False
             ctx.tp = None
             ctx.in_bufs = ctx.outs = None
         return res
@@ -522,6 +542,8 @@ class _TapeFn(torch.autograd.Function):
             g = tp.grad(b) if need else None
             gin.append(g.nchw() if g is not None else None)
         gp = [tp.pgrads.get(p) if p.requires_grad else None for p in ctx.params]
+        for ent in tp.repacked:
+            ent[4] = False
         ctx.tp = ctx.in_bufs = ctx.outs = None
         return (None, None, None, None) + tuple(gin) + tuple(gp)
 

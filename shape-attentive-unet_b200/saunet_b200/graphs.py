@@ -1,0 +1,50 @@
+"""CUDA-graph capture of one whole training step (forward + DualLoss + metrics + backward).
+
+The step is ~1300 short kernel launches issued from Python; eagerly the GPU idles at every host synchronisation
+(`loss.item()` in train.py:114) while the host re-issues them.  ``GraphedStep`` captures the launches once and
+replays them with a single `cudaGraphLaunch`: inputs are copied into static device buffers (the H2D copy of the
+step), gradients land in the module's flat ``GradArena`` and the loss in a static tensor.
+
+Only launches are captured -- the arithmetic is the same libsaunet_b200.so kernels.  The weight-packing cache is
+bypassed during capture so the pack kernels are part of the graph (weights change every optimizer step).
+"""
+import torch
+
+from . import engine
+
+
+class GraphedStep:
+    def __init__(self, seg_module, arena, example_feed, epoch=0, warmup=2):
+        """seg_module: models.SegmentationModule on a CUDA device; arena: parallel.GradArena of its unet;
+        example_feed: dict(image, seg, edge) device tensors with the shapes of every later step."""
+        self.seg_module, self.arena = seg_module, arena
+        self.static = {k: v.clone() for k, v in example_feed.items()}
+        dev = self.static["image"].device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                     # warm-up on the side stream (lazy inits, allocator pools)
+            for _ in range(warmup):
+                self._eager(epoch)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        engine.FORCE_PACK = True
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss, self.acc = self._eager(epoch)
+        finally:
+            engine.FORCE_PACK = False
+
+    def _eager(self, epoch):
+        s = self.static
+        self.arena.zero()
+        loss, acc = self.seg_module({"image": s["image"], "mask": (s["seg"], s["edge"])}, epoch)
+        loss.backward()
+        return loss.detach(), acc
+
+    def __call__(self, feed):
+        """feed tensors may live on the host (pinned) or the device; returns the (static) loss tensor."""
+        for k, v in feed.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss

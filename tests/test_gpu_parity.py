@@ -294,3 +294,44 @@ def test_no_cpu_fallback():
         m = SAUNet(num_classes=4, pretrained=False)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 64, 64))
+
+
+def test_graphed_step_matches_eager():
+    """saunet_b200.graphs.GraphedStep (CUDA-graph replay of fwd+loss+bwd) reproduces the eager step: same loss and
+    gradients, picks up in-place weight updates (the pack kernels are inside the graph) and new inputs."""
+    from models import SegmentationModule
+    from loss import DualLoss
+    from saunet_b200.graphs import GraphedStep
+    from saunet_b200.parallel import GradArena
+    unet = _model(True)
+    seg_mod = SegmentationModule(DualLoss(), unet, 4).to(DEV).train()
+    arena = GradArena(unet)
+    d0 = {k: v.to(DEV) for k, v in synth.synthetic_batch(2, 64, seed=304).items()}
+    d1 = {k: v.to(DEV) for k, v in synth.synthetic_batch(2, 64, seed=7).items()}
+
+    def eager(d):
+        arena.zero()
+        loss, _ = seg_mod({"image": d["image"], "mask": (d["seg"], d["edge"])}, 0)
+        loss.backward()
+        torch.cuda.synchronize()
+        return float(loss), arena.flat.clone()
+
+    bn_state = {k: v.clone() for k, v in unet.state_dict().items() if "running" in k or "num_batches" in k}
+    g = GraphedStep(seg_mod, arena, d0)
+    unet.load_state_dict(bn_state, strict=False)          # undo the warm-up's running-stat updates
+    with torch.no_grad():
+        for p in unet.parameters():
+            p.mul_(1.01)                                  # an "optimizer step": in-place, bumps the version counters
+    for d in (d1, d0):
+        unet.load_state_dict(bn_state, strict=False)
+        le, ge = eager(d)
+        unet.load_state_dict(bn_state, strict=False)
+        lg = float(g(d))
+        torch.cuda.synchronize()
+        assert abs(lg - le) < 1e-5 * abs(le), (lg, le)
+        # same kernels, but fp32 atomics land in a different order and the deep gradients are chaotic (see
+        # _grad_noise): the top of the network must agree tightly, the whole arena in norm
+        o = arena.offsets[id(unet.final.weight)]
+        n = unet.final.weight.numel()
+        assert rel_err(arena.flat[o:o + n].cpu(), ge[o:o + n].cpu()) < 1e-3
+        assert float((arena.flat - ge).norm() / ge.norm()) < 5e-2
