@@ -114,6 +114,16 @@ WG_CASES = [
     (2, 8, 8, 512, 256, 3, 1, -1, False, 0, 0),       # several M / N tiles
     (3, 24, 24, 16, 8, 1, 1, 0, False, 0, 0),         # tiny channel counts
     (2, 6, 5, 64, 32, 4, 2, -1, False, 0, 0),         # conv-transpose wgrad: P = x (low-res), Q = dY gathered at stride 2
+    # 3x3 / s1 / p1 with H % 8 == 0, W % 8 == 0, Ca <= 64 -> the all-taps halo kernel (conv_wgrad_halo.cu)
+    (2, 16, 24, 32, 128, 3, 1, -1, True, 96, 0),      # dense conv2: dY is a slice of the concat-buffer gradient
+    (3, 8, 8, 32, 128, 3, 1, -1, True, 0, 0),         # one tile per image (all-border halo)
+    (1, 32, 16, 64, 64, 3, 1, -1, True, 0, 0),        # BasicBlock: 64-wide dY -> two tap groups
+    (2, 16, 16, 32, 32, 3, 1, -1, False, 0, 0),       # res2: one Q plane
+    (2, 24, 8, 16, 16, 3, 1, -1, True, 0, 0),         # res3: half planes on both sides
+    (1, 16, 16, 48, 64, 3, 1, -1, False, 0, 0),       # dec1 3x3: Ca = 48
+    (2, 16, 16, 32, 160, 3, 1, -1, False, 0, 32),     # two M tiles, the second partial
+    (4, 128, 128, 32, 64, 3, 1, -1, False, 0, 0),     # dec0-like; 7 tiles per CTA (stage ring wraps around)
+    (2, 128, 64, 64, 64, 3, 1, -1, True, 0, 0),       # res1-like; 4 tiles per CTA in each tap group
 ]
 
 
