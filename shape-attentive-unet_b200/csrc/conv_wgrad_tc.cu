@@ -296,7 +296,7 @@ bool conv_wgrad_tc_eligible(const saunet_wgrad_desc* d) {
     if (d->precision != 1) return false;
     if (d->Ca % 4 || d->Cb % 4 || d->p_ld % 4 || d->q_ld % 4 || !aligned16(d->p) || !aligned16(d->q)) return false;
     if (d->q_scale && (!aligned16(d->q_scale) || !aligned16(d->q_shift))) return false;
-    if (d->Ca < 8 || d->Cb < 8) return false;
+    if (d->Ca < 8 || d->Cb < 4 || d->KH * d->KW * d->Cb < 32) return false;     // (Cb = 4: the channel-padded 7x7 stem)
     const long long M = (long long)d->B * d->Hg * d->Wg;                       // 32-bit element offsets in the kernel
     if (M * d->p_ld >= (1ll << 31) || (long long)d->B * d->Hq * d->Wq * d->q_ld >= (1ll << 31)) return false;
     return true;

@@ -2,6 +2,7 @@
 // affine+activation apply, and the two-pass backward (reduce, apply).  All HBM-bound: coalesced
 // 128-bit loads along the channel axis, fp64 accumulation of the per-channel sums.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace saunet {
 
@@ -222,6 +223,170 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
     }
 }
 
+
+// ---- BatchNorm backward, 4-channel vector path -------------------------------------------------------------------
+// Thread = one fixed 4-channel group (its BN constants live in registers) x a strided set of pixels; 4 pixels per
+// iteration with all 128-bit loads issued before the math (8-12 loads in flight per thread).  Per-thread sums are
+// fp32 over at most 32 pixels, then folded into fp64.
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4rw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+struct BnGeom {
+    int lanes, rows;
+    __device__ BnGeom(int L) { lanes = L < 256 ? L : 256; rows = 256 / lanes; }
+};
+
+template <bool RELU, bool HAS_OUT>
+__device__ __forceinline__ float4 masked_grad(float4 g, float4 xv, float4 ov, float4 sc, float4 sh) {
+    if (RELU) {
+        float4 z;
+        if (HAS_OUT) z = ov;
+        else { z.x = fmaf(xv.x, sc.x, sh.x); z.y = fmaf(xv.y, sc.y, sh.y); z.z = fmaf(xv.z, sc.z, sh.z); z.w = fmaf(xv.w, sc.w, sh.w); }
+        if (!(z.x > 0.f)) g.x = 0.f;
+        if (!(z.y > 0.f)) g.y = 0.f;
+        if (!(z.z > 0.f)) g.z = 0.f;
+        if (!(z.w > 0.f)) g.w = 0.f;
+    }
+    return g;
+}
+
+template <bool RELU, bool HAS_OUT>
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce4_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ x, int x_ld,
+                                                             const float* __restrict__ out, int out_ld, const float* __restrict__ state,
+                                                             int C, long long npix, double* __restrict__ red) {
+    __shared__ double sred[8 * 256];
+    const int L = C >> 2;
+    const BnGeom gm(L);
+    const int tid = threadIdx.x, l = tid % gm.lanes, r = tid / gm.lanes;
+    const bool active = r < gm.rows;
+    const long long stride = (long long)gridDim.x * gm.rows;
+    for (int l0 = 0; l0 < L; l0 += gm.lanes) {
+        const int lg = l0 + l;
+        const bool on = active && lg < L;
+        const int c = lg * 4;
+        double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
+        if (on) {
+            const float4 sc = ld4(state + c), sh = ld4(state + C + c), mean = ld4(state + 2 * C + c), istd = ld4(state + 3 * C + c);
+            long long p = (long long)blockIdx.x * gm.rows + r;
+            while (p < npix) {
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int it = 0; it < 8 && p < npix; ++it, p += 4 * stride) {
+                    float4 g[4], xv[4], ov[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const long long pp = p + u * stride;
+                        const bool ok = pp < npix;
+                        g[u] = ok ? ld4(dy + (size_t)pp * dy_ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        xv[u] = ok ? ld4(x + (size_t)pp * x_ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (RELU && HAS_OUT) ov[u] = ok ? ld4(out + (size_t)pp * out_ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 gg = masked_grad<RELU, HAS_OUT>(g[u], xv[u], ov[u], sc, sh);
+                        s1[0] += gg.x; s1[1] += gg.y; s1[2] += gg.z; s1[3] += gg.w;
+                        s2[0] = fmaf(gg.x, (xv[u].x - mean.x) * istd.x, s2[0]); s2[1] = fmaf(gg.y, (xv[u].y - mean.y) * istd.y, s2[1]);
+                        s2[2] = fmaf(gg.z, (xv[u].z - mean.z) * istd.z, s2[2]); s2[3] = fmaf(gg.w, (xv[u].w - mean.w) * istd.w, s2[3]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a1[e] += (double)s1[e]; a2[e] += (double)s2[e]; }
+            }
+        }
+        if (gm.rows > 1) {
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { sred[e * 256 + tid] = a1[e]; sred[(4 + e) * 256 + tid] = a2[e]; }
+            __syncthreads();
+            if (r == 0 && lg < L) {
+                for (int rr = 1; rr < gm.rows; ++rr)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { a1[e] += sred[e * 256 + rr * gm.lanes + l]; a2[e] += sred[(4 + e) * 256 + rr * gm.lanes + l]; }
+            }
+        }
+        if (r == 0 && lg < L) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { atomicAdd(red + c + e, a1[e]); atomicAdd(red + C + c + e, a2[e]); }
+        }
+    }
+}
+
+template <bool RELU, bool HAS_OUT>
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply4_kernel(const float* __restrict__ dy, int dy_ld, const float* __restrict__ x, int x_ld,
+                                                            const float* __restrict__ out, int out_ld, const float* __restrict__ state,
+                                                            const float* __restrict__ gamma, const double* __restrict__ red, int C,
+                                                            long long npix, int training, float* dx, int dx_ld, int dx_acc,
+                                                            float* dres, int dres_ld, int dres_acc, float* dgamma, float* dbeta) {
+    const int L = C >> 2;
+    const BnGeom gm(L);
+    const int tid = threadIdx.x, l = tid % gm.lanes, r = tid / gm.lanes;
+    if (blockIdx.x == 0 && dgamma) {
+        for (int c = tid; c < C; c += blockDim.x) { dbeta[c] += (float)red[c]; dgamma[c] += (float)red[C + c]; }
+    }
+    if (r >= gm.rows) return;
+    const long long stride = (long long)gridDim.x * gm.rows;
+    const double inv_n = 1.0 / (double)npix;
+    for (int l0 = 0; l0 < L; l0 += gm.lanes) {
+        const int lg = l0 + l;
+        if (lg >= L) continue;
+        const int c = lg * 4;
+        const float4 sc = ld4(state + c), sh = ld4(state + C + c), mean = ld4(state + 2 * C + c), istd = ld4(state + 3 * C + c);
+        // dx = gs*g - gs*m1 - (gs*m2*invstd) * (x - mean)
+        float gs[4], gm1[4], kk[4];
+        {
+            const float is[4] = {istd.x, istd.y, istd.z, istd.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                gs[e] = (gamma ? __ldg(gamma + c + e) : 1.f) * is[e];
+                const float m1 = training ? (float)(red[c + e] * inv_n) : 0.f, m2 = training ? (float)(red[C + c + e] * inv_n) : 0.f;
+                gm1[e] = gs[e] * m1; kk[e] = gs[e] * m2 * is[e];
+            }
+        }
+        for (long long p = (long long)blockIdx.x * gm.rows + r; p < npix; p += 2 * stride) {
+            float4 g[2], xv[2], ov[2], od[2], orr[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const long long pp = p + u * stride;
+                if (pp < npix) {
+                    g[u] = ld4(dy + (size_t)pp * dy_ld + c);
+                    xv[u] = ld4(x + (size_t)pp * x_ld + c);
+                    if (RELU && HAS_OUT) ov[u] = ld4(out + (size_t)pp * out_ld + c);
+                    if (dx && dx_acc) od[u] = ld4rw(dx + (size_t)pp * dx_ld + c);
+                    if (dres && dres_acc) orr[u] = ld4rw(dres + (size_t)pp * dres_ld + c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const long long pp = p + u * stride;
+                if (pp < npix) {
+                    const float4 gg = masked_grad<RELU, HAS_OUT>(g[u], xv[u], ov[u], sc, sh);
+                    if (dx) {
+                        float4 o;
+                        o.x = fmaf(gs[0], gg.x, fmaf(-kk[0], xv[u].x - mean.x, -gm1[0]));
+                        o.y = fmaf(gs[1], gg.y, fmaf(-kk[1], xv[u].y - mean.y, -gm1[1]));
+                        o.z = fmaf(gs[2], gg.z, fmaf(-kk[2], xv[u].z - mean.z, -gm1[2]));
+                        o.w = fmaf(gs[3], gg.w, fmaf(-kk[3], xv[u].w - mean.w, -gm1[3]));
+                        if (dx_acc) { o.x += od[u].x; o.y += od[u].y; o.z += od[u].z; o.w += od[u].w; }
+                        *reinterpret_cast<float4*>(dx + (size_t)pp * dx_ld + c) = o;
+                    }
+                    if (dres) {
+                        float4 o = gg;
+                        if (dres_acc) { o.x += orr[u].x; o.y += orr[u].y; o.z += orr[u].z; o.w += orr[u].w; }
+                        *reinterpret_cast<float4*>(dres + (size_t)pp * dres_ld + c) = o;
+                    }
+                }
+            }
+        }
+    }
+}
+
+static inline int bn_blocks(int C, long long npix) {
+    const int L = C / 4, lanes = L < 256 ? L : 256, rows = 256 / lanes;
+    long long want = (npix + (long long)rows * 8 - 1) / ((long long)rows * 8);        // >= 8 pixels per thread when possible
+    long long cap = (long long)kNumSMs * 2;          // two resident CTAs per SM (<= 128 registers): one wave
+    if (want < 1) want = 1;
+    return (int)(want > cap ? cap : want);
+}
+
 static inline int ew_blocks(long long n) {
     long long b = (n + 255) / 256; long long cap = (long long)kNumSMs * 16;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
@@ -281,7 +446,16 @@ extern "C" int saunet_affine_act(const float* x, int x_ld, const float* scale, c
 extern "C" int saunet_bn_bwd_reduce(const float* dy, int dy_ld, const float* x, int x_ld, const float* out, int out_ld,
                                     const float* state, int C, long long npix, int act, double* red, void* stream) {
     SAUNET_CHECK_ARG(dy && x && state && red && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "bn_bwd_reduce: bad args");
-    bool vec = vec_ok(C, {{dy, dy_ld}, {x, x_ld}, {out, out_ld}});
+    bool vec = vec_ok(C, {{dy, dy_ld}, {x, x_ld}, {out, out_ld}}) && aligned16(state);
+    if (vec && !getenv("SAUNET_NO_BN4")) {
+        const int blocks = bn_blocks(C, npix);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (act != SAUNET_ACT_RELU) bn_bwd_reduce4_kernel<false, false><<<blocks, 256, 0, st>>>(dy, dy_ld, x, x_ld, out, out_ld, state, C, npix, red);
+        else if (out) bn_bwd_reduce4_kernel<true, true><<<blocks, 256, 0, st>>>(dy, dy_ld, x, x_ld, out, out_ld, state, C, npix, red);
+        else bn_bwd_reduce4_kernel<true, false><<<blocks, 256, 0, st>>>(dy, dy_ld, x, x_ld, out, out_ld, state, C, npix, red);
+        SAUNET_CHECK_LAUNCH("bn_bwd_reduce4_kernel");
+        return SAUNET_OK;
+    }
     BnBwdOp<1> o1{dy, dy_ld, x, x_ld, out, out_ld, state, C, act};
     BnBwdOp<4> o4{dy, dy_ld, x, x_ld, out, out_ld, state, C, act};
     return launch_reduce(o1, o4, vec, C, npix, red, (long long)C, (cudaStream_t)stream, "bn_bwd_reduce_kernel");
@@ -294,6 +468,17 @@ extern "C" int saunet_bn_bwd_apply(const float* dy, int dy_ld, const float* x, i
     SAUNET_CHECK_ARG(dy && x && state && red && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "bn_bwd_apply: bad args");
     SAUNET_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), SAUNET_ERR_BAD_SHAPE, "bn_bwd_apply: dgamma/dbeta mismatch");
     bool vec = vec_ok(C, {{dy, dy_ld}, {x, x_ld}, {out, out_ld}, {dx, dx_ld}, {dres, dres_ld}});
+    if (vec && aligned16(state) && !getenv("SAUNET_NO_BN4")) {
+        const int blocks = bn_blocks(C, npix);
+        cudaStream_t st = (cudaStream_t)stream;
+#define SAUNET_BN_APPLY(R, O) bn_bwd_apply4_kernel<R, O><<<blocks, 256, 0, st>>>(dy, dy_ld, x, x_ld, out, out_ld, state, gamma, red, C, npix, training, dx, dx_ld, dx_acc, dres, dres_ld, dres_acc, dgamma, dbeta)
+        if (act != SAUNET_ACT_RELU) SAUNET_BN_APPLY(false, false);
+        else if (out) SAUNET_BN_APPLY(true, true);
+        else SAUNET_BN_APPLY(true, false);
+#undef SAUNET_BN_APPLY
+        SAUNET_CHECK_LAUNCH("bn_bwd_apply4_kernel");
+        return SAUNET_OK;
+    }
     if (vec) bn_bwd_apply_kernel<4><<<ew_blocks(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(dy, dy_ld, x, x_ld, out, out_ld, state, gamma, red, C, npix, act, training, dx, dx_ld, dx_acc, dres, dres_ld, dres_acc, dgamma, dbeta);
     else bn_bwd_apply_kernel<1><<<ew_blocks(npix * C), 256, 0, (cudaStream_t)stream>>>(dy, dy_ld, x, x_ld, out, out_ld, state, gamma, red, C, npix, act, training, dx, dx_ld, dx_acc, dres, dres_ld, dres_acc, dgamma, dbeta);
     SAUNET_CHECK_LAUNCH("bn_bwd_apply_kernel");

@@ -114,6 +114,7 @@ WG_CASES = [
     (2, 8, 8, 512, 256, 3, 1, -1, False, 0, 0),       # several M / N tiles
     (3, 24, 24, 16, 8, 1, 1, 0, False, 0, 0),         # tiny channel counts
     (2, 6, 5, 64, 32, 4, 2, -1, False, 0, 0),         # conv-transpose wgrad: P = x (low-res), Q = dY gathered at stride 2
+    (2, 16, 16, 64, 4, 7, 2, -3, False, 0, 0),        # the 7x7 / stride 2 stem on its 4-channel padded input
     # 3x3 / s1 / p1 with H % 8 == 0, W % 8 == 0, Ca <= 64 -> the all-taps halo kernel (conv_wgrad_halo.cu)
     (2, 16, 24, 32, 128, 3, 1, -1, True, 96, 0),      # dense conv2: dY is a slice of the concat-buffer gradient
     (3, 8, 8, 32, 128, 3, 1, -1, True, 0, 0),         # one tile per image (all-border halo)
