@@ -1,21 +1,29 @@
 // conv_tc.cu -- implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators).
 //
-// GEMM view (same descriptor as conv_simt.cu): rows = 128 output pixels per CTA, N = Cout tile (16..256),
+// GEMM view (same descriptor as conv_simt.cu): rows = 128 output pixels per tile, N = Cout tile (16..256),
 // K = KH*KW*Cin in blocks of 32 fp32 (= one 128-byte swizzle row).
 //
-// Warp roles (192 threads, one output tile per CTA):
-//   warps 0-3  A producers: gather the im2col rows from NHWC global memory (128-bit loads), apply the fused
-//              BatchNorm+ReLU prologue, split every value into tf32 hi + lo, store both tiles into shared
-//              memory in the UMMA K-major SWIZZLE_128B layout, fence.proxy.async, arrive on full_a[stage].
-//              After the main loop the same warps run the epilogue (tcgen05.ld -> bias / BN-statistics /
-//              gate row-scale / activation -> global).
-//   warp 4     allocates TMEM; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8):
-//              3xTF32 = a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with fp32 accumulation in TMEM (error ~2^-21, the
-//              accuracy class the 1e-4 parity gate needs), or one pass (plain TF32) on request.
-//   warp 5     one lane streams the pre-tiled, pre-swizzled, pre-split weight tiles with cp.async.bulk (TMA
-//              engine, 1-D bulk copy) completing on full_b[stage].
-// Pipeline: NSTAGE-deep ring, mbarrier full/empty per stage, tcgen05.commit releases a stage.
+// PERSISTENT kernel: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  All roles run flat loops
+// over (tile, k-block), so the pipelines never drain at a tile boundary and the epilogue of tile i overlaps the main
+// loop of tile i+1 through two TMEM accumulator buffers (the DenseNet 1x1 layers have only 2..31 k-blocks per tile:
+// a one-tile-per-CTA kernel spends half its life in prologue + epilogue; ncu: 14 % tensor-active).
+//
+// Warp roles (832 threads):
+//   warps 0-15   A producers: gather the im2col rows from NHWC global memory (128-bit loads), apply the fused
+//                BatchNorm+ReLU prologue, split every value into tf32 hi + lo, store both tiles into shared
+//                memory in the UMMA K-major SWIZZLE_128B layout, fence.proxy.async, arrive on full_a[stage].
+//                A 3-deep register ring keeps two k-blocks of gathers in flight, across tile boundaries too.
+//   warps 16-23  epilogue: tcgen05.ld -> bias / BN-statistics / gate row-scale / activation -> global, then
+//                release the accumulator buffer (tmem_empty).
+//   warp 24      allocates TMEM; one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8):
+//                3xTF32 = a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation in TMEM (error ~2^-21, the
+//                accuracy class the 1e-4 parity gate needs), or one pass (plain TF32) on request.
+//   warp 25      one lane streams the pre-tiled, pre-swizzled, pre-split weight tiles with cp.async.bulk (TMA
+//                engine, 1-D bulk copy) completing on full_b[stage].
+// Pipeline: NSTAGE-deep smem ring (mbarrier full/empty per stage, tcgen05.commit releases a stage) + 2 accumulator
+// buffers (tmem_full / tmem_empty).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 extern "C" int saunet_tc_chunk_major(int taps, int Cin);
 
@@ -24,8 +32,10 @@ namespace saunet {
 struct TcP {
     saunet_conv_desc d;
     int M, K, HgWg, nkb;
+    int ntile_n, ntiles;
     int chunk_major;      // K ordered (32-channel chunk, tap, channel) instead of (tap, channel): see pack_tc_kernel
     const float* wt;      // tiled weights: [n_tile][k_block][pass][BN][32] (swizzled image)
+    long long* prof;      // optional per-CTA cycle counters (tools/bench_conv.py, SAUNET_TC_PROF)
 };
 
 template <int BN, int NPASS>
@@ -34,46 +44,58 @@ struct TcCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int NOP = (NPASS == 3) ? 2 : 1;                 // hi (+ lo) images per operand
     static constexpr int STAGE = NOP * (A_BYTES + B_BYTES);
-    // narrow tiles: 2 smem stages (the register ring hides the gather latency) so that two CTAs share an SM and one
-    // CTA's epilogue overlaps the other's main loop; wide tiles: as many stages as fit, one CTA per SM
-    static constexpr int NSTAGE_RAW = (192 * 1024) / STAGE;
-    static constexpr int NSTAGE = (2 * STAGE <= 100 * 1024) ? 2 : (NSTAGE_RAW > 4 ? 4 : (NSTAGE_RAW < 2 ? 2 : NSTAGE_RAW));
-    static constexpr int MIN_CTAS = (2 * STAGE <= 100 * 1024) ? 2 : 1;
-    static constexpr int SMEM = NSTAGE * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int NSTAGE_RAW = (196 * 1024) / STAGE;
+    static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : (NSTAGE_RAW < 2 ? 2 : NSTAGE_RAW);
+    static constexpr int RED_BYTES = 8 * BN * 4;                     // [4 lane quarters][sum, sumsq][BN] floats
+    static constexpr int SMEM = NSTAGE * STAGE + RED_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    static constexpr int NBUF = 2;                                   // accumulator buffers (epilogue overlap)
     // The tensor core rounds its fp32 accumulator toward zero on every MMA, a bias that grows linearly with K
     // (measured 4.5e-9*K normalised).  Round-robin the k-blocks over NACC TMEM accumulators and add them in the
     // epilogue with round-to-nearest FADDs: the bias drops by ~NACC.
-    static constexpr int NACC = ((512 / MIN_CTAS) / ACC_COLS) > 4 ? 4 : ((512 / MIN_CTAS) / ACC_COLS);
-    static constexpr int TMEM_COLS = NACC * ACC_COLS;
+    static constexpr int NACC = (512 / (NBUF * ACC_COLS)) > 4 ? 4 : (512 / (NBUF * ACC_COLS));
+    static constexpr int BUF_COLS = NACC * ACC_COLS;
+    static constexpr int TMEM_COLS = NBUF * BUF_COLS <= 256 ? 256 : 512;
 };
 
-constexpr int kProducers = 256;      // 8 producer / epilogue warps
-constexpr int kTcThreads = kProducers + 64;
+constexpr int kProducers = 512;      // 16 producer warps (warps 0-15): 2 rows x one 16-byte chunk per thread and k-block
+constexpr int kEpilogue = 256;       // 8 epilogue warps (warps 16-23)
+constexpr int kTcThreads = kProducers + kEpilogue + 64;     // + MMA warp (24) + weight loader warp (25)
+constexpr int kRowsPerThread = 128 * 8 / kProducers;        // 2
 
-template <int BN, int NPASS>
-__global__ void __launch_bounds__(kTcThreads, TcCfg<BN, NPASS>::MIN_CTAS) conv_tc_kernel(const __grid_constant__ TcP p) {
+#define TC_PROF_T0() long long pt0__ = p.prof ? clock64() : 0
+#define TC_PROF_ADD(var) do { if (p.prof) { long long t1__ = clock64(); (var) += t1__ - pt0__; pt0__ = t1__; } } while (0)
+
+// MODE 0: generic K order (tap-major, any Cin % 4 == 0; per-chunk tap via integer division)
+// MODE 1: pointwise 1x1 / stride 1 / no padding -- no taps, no spatial bounds (the DenseNet bottleneck convs and their dgrads)
+// MODE 2: chunk-major K order (taps > 1, Cin % 32 == 0): (chunk, tap) advance incrementally, no divisions
+template <int BN, int NPASS, int MODE>
+__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcP p) {
     using Cfg = TcCfg<BN, NPASS>;
     constexpr int NSTAGE = Cfg::NSTAGE;
     constexpr int NACC = Cfg::NACC;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-    const uint32_t bars = sbase + NSTAGE * Cfg::STAGE;
+    float* red = reinterpret_cast<float*>(sgen + NSTAGE * Cfg::STAGE);
+    const uint32_t bars = sbase + NSTAGE * Cfg::STAGE + Cfg::RED_BYTES;
     auto full_a = [&](int s) { return bars + 8u * s; };
     auto full_b = [&](int s) { return bars + 8u * (NSTAGE + s); };
     auto empty = [&](int s) { return bars + 8u * (2 * NSTAGE + s); };
-    const uint32_t accum_bar = bars + 8u * (3 * NSTAGE);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + NSTAGE * Cfg::STAGE + 8 * (3 * NSTAGE + 1));
+    auto tmem_full = [&](int b) { return bars + 8u * (3 * NSTAGE + b); };
+    auto tmem_empty = [&](int b) { return bars + 8u * (3 * NSTAGE + 2 + b); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + NSTAGE * Cfg::STAGE + Cfg::RED_BYTES + 8 * (3 * NSTAGE + 4));
 
     const saunet_conv_desc& d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * 128, n0 = blockIdx.y * BN;
-    constexpr int MMA_WARP = kProducers / 32, LOAD_WARP = MMA_WARP + 1;
+    constexpr int NPW = kProducers / 32, EPI_WARP0 = NPW, MMA_WARP = NPW + kEpilogue / 32, LOAD_WARP = MMA_WARP + 1;
+    constexpr int RPT = kRowsPerThread, RSTEP = 128 / RPT;
+    const int my_tiles = (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;    // >= 1 (grid <= ntiles)
+    const int nkb = p.nkb;
 
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_a(s), kProducers / 32); mbar_init(full_b(s), 1); mbar_init(empty(s), 1); }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), kEpilogue / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -84,215 +106,291 @@ __global__ void __launch_bounds__(kTcThreads, TcCfg<BN, NPASS>::MIN_CTAS) conv_t
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const long long kt0 = p.prof ? clock64() : 0;
 
-    if (warp < MMA_WARP) {
-        // ================= A producer =================
-        const int chunk = tid & 7, rbase = tid >> 3;          // 4 rows per thread: rbase + 32*i
-        // per-row constants: element offset of (b, iy0, ix0) and the tap-(0,0) coordinates; rows past M get
-        // coordinates that fail every bounds test.  32-bit element offsets (host guarantees the tensor fits).
-        int r_iy0[4], r_ix0[4], r_base[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = m0 + rbase + 32 * i;
-            if (m < p.M) {
-                int b = m / p.HgWg; int r = m - b * p.HgWg; int gi = r / d.Wg; int gj = r - gi * d.Wg;
-                r_iy0[i] = gi * d.sy + d.offy; r_ix0[i] = gj * d.sx + d.offx;
-                r_base[i] = ((b * d.Hin + r_iy0[i]) * d.Win + r_ix0[i]) * d.x_ld;
-            } else { r_iy0[i] = -(1 << 28); r_ix0[i] = -(1 << 28); r_base[i] = 0; }
-        }
+    if (warp < NPW) {
+        // ================= A producers =================
+        const int chunk = tid & 7, rbase = tid >> 3;          // RPT rows per thread: rbase + RSTEP*i
         const int taps = d.KH * d.KW;
-        // gather of one k-block into registers (padding tagged with a quiet NaN so it stays zero after the prologue)
-        auto load_block = [&](int kb, float4 (&v)[4], int& cch) {
-            int c, tap; bool kval;
-            if (p.chunk_major) { const int cc = kb / taps; tap = kb - cc * taps; c = cc * 32 + chunk * 4; kval = true; }
-            else { const int k = kb * 32 + chunk * 4; kval = k < p.K; tap = kval ? k / d.Cin : 0; c = k - tap * d.Cin; }
-            const int ky = tap / d.KW, kx = tap - ky * d.KW;
-            const int tapoff = (ky * d.Win + kx) * d.x_ld + c;
-            cch = kval ? c : -1;
+        const int total = my_tiles * nkb;
+        long long pw_empty = 0, pw_store = 0, pw_load = 0;
+        // load cursor: (tile index in this CTA's list, k-block) of the next gather + that tile's per-row constants:
+        // element offset of (b, iy0, ix0) and the tap-(0,0) coordinates; rows past M fail every bounds test.
+        // 32-bit element offsets (host guarantees the tensor fits).  The loop runs flat over (tile, k-block).
+        int l_ti = -1, l_kb = 0, l_next_ti = 0;
+        int l_tap = 0, l_ky = 0, l_kx = 0, l_cc = 0;          // MODE 2 cursor: tap (ky, kx) within the 32-channel chunk l_cc
+        int r_iy0[RPT], r_ix0[RPT], r_base[RPT];
+        uint32_t s_off[RPT];                                  // swizzled byte offset of this thread's chunk in each of its rows
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const bool ok = kval && (unsigned)(r_iy0[i] + ky) < (unsigned)d.Hin && (unsigned)(r_ix0[i] + kx) < (unsigned)d.Win;
-                v[i] = make_float4(__int_as_float(0x7fc00001), 0.f, 0.f, 0.f);
-                if (ok) v[i] = __ldg(reinterpret_cast<const float4*>(d.x + (r_base[i] + tapoff)));
+        for (int i = 0; i < RPT; ++i) {
+            const int r = rbase + RSTEP * i;
+            s_off[i] = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+        }
+        auto set_tile = [&](int ti) {
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int m0 = (tile / p.ntile_n) * 128;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const int m = m0 + rbase + RSTEP * i;
+                if (m < p.M) {
+                    if (MODE == 1) { r_iy0[i] = 0; r_ix0[i] = 0; r_base[i] = m * d.x_ld; }
+                    else {
+                        int b = m / p.HgWg; int r = m - b * p.HgWg; int gi = r / d.Wg; int gj = r - gi * d.Wg;
+                        r_iy0[i] = gi * d.sy + d.offy; r_ix0[i] = gj * d.sx + d.offx;
+                        r_base[i] = ((b * d.Hin + r_iy0[i]) * d.Win + r_ix0[i]) * d.x_ld;
+                    }
+                } else { r_iy0[i] = -(1 << 28); r_ix0[i] = -(1 << 28); r_base[i] = -1; }
             }
+            l_ti = ti;
         };
-        auto store_block = [&](int kb, const float4 (&v)[4], int cch) {
-            const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
+        // gather of the next k-block into registers; `tag` = channel of the thread's chunk (0xFFFFF: K padding) in the low
+        // bits and one validity bit per row above them (padding / out-of-image rows stay exactly zero after the prologue)
+        auto load_next = [&](float4 (&v)[RPT], int& tag) {
+            if (l_next_ti >= my_tiles) return;
+            if (l_next_ti != l_ti) set_tile(l_next_ti);
+            const int kb = l_kb;
+            int c, ky = 0, kx = 0; bool kval = true;
+            if (MODE == 1) { c = kb * 32 + chunk * 4; kval = c < d.Cin; }
+            else if (MODE == 2) { c = l_cc * 32 + chunk * 4; ky = l_ky; kx = l_kx; }
+            else { const int k = kb * 32 + chunk * 4; kval = k < p.K; const int tap = kval ? k / d.Cin : 0; c = k - tap * d.Cin; ky = tap / d.KW; kx = tap - ky * d.KW; }
+            if (++l_kb == nkb) { l_kb = 0; ++l_next_ti; l_tap = 0; l_ky = 0; l_kx = 0; l_cc = 0; }
+            else if (MODE == 2) {
+                if (++l_tap == taps) { l_tap = 0; l_ky = 0; l_kx = 0; ++l_cc; }
+                else if (++l_kx == d.KW) { l_kx = 0; ++l_ky; }
+            }
+            const int tapoff = (MODE == 1) ? c : (ky * d.Win + kx) * d.x_ld + c;
+            int t = kval ? c : 0xFFFFF;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                bool ok;
+                if (MODE == 1) ok = kval && r_base[i] >= 0;
+                else ok = kval && (unsigned)(r_iy0[i] + ky) < (unsigned)d.Hin && (unsigned)(r_ix0[i] + kx) < (unsigned)d.Win;
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) { v[i] = __ldg(reinterpret_cast<const float4*>(d.x + (r_base[i] + tapoff))); t |= (1 << (20 + i)); }
+            }
+            tag = t;
+        };
+        auto store_item = [&](int f, const float4 (&v)[RPT], int tag) {
+            const int s = f % NSTAGE; const uint32_t ph = (f / NSTAGE) & 1;
+            const int cch = tag & 0xFFFFF;
             float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (d.in_scale && cch >= 0) {
+            if (d.in_scale && cch != 0xFFFFF) {
                 sc = __ldg(reinterpret_cast<const float4*>(d.in_scale + cch));
                 sh = __ldg(reinterpret_cast<const float4*>(d.in_shift + cch));
             }
+            TC_PROF_T0();
             mbar_wait(empty(s), ph ^ 1u);
+            TC_PROF_ADD(pw_empty);
             uint8_t* a_hi = sgen + s * Cfg::STAGE;
             uint8_t* a_lo = a_hi + Cfg::A_BYTES;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < RPT; ++i) {
                 float4 t = v[i];
-                if (__float_as_int(t.x) == 0x7fc00001) t = make_float4(0.f, 0.f, 0.f, 0.f);
-                else if (d.in_scale) {
+                if (d.in_scale && (tag & (1 << (20 + i)))) {
                     t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
                     if (d.in_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
                 }
-                const int r = rbase + 32 * i;
-                const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
                 float4 hi = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
-                *reinterpret_cast<float4*>(a_hi + off) = hi;
+                *reinterpret_cast<float4*>(a_hi + s_off[i]) = hi;
                 if (NPASS == 3) {
                     float4 lo = make_float4(tf32_hi(t.x - hi.x), tf32_hi(t.y - hi.y), tf32_hi(t.z - hi.z), tf32_hi(t.w - hi.w));
-                    *reinterpret_cast<float4*>(a_lo + off) = lo;
+                    *reinterpret_cast<float4*>(a_lo + s_off[i]) = lo;
                 }
             }
+            TC_PROF_ADD(pw_load);          // (first use of the gathered registers: global-load latency lands here)
             // every writer fences its own generic-proxy stores towards the async proxy, the warp converges, and ONE
-            // lane arrives (256 per-thread arrivals on one mbarrier serialise in shared memory)
+            // lane arrives (per-thread arrivals on one mbarrier serialise in shared memory)
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_a(s));
+            TC_PROF_ADD(pw_store);
         };
         // software pipeline: a 3-deep register ring keeps two k-blocks of gathers in flight while one is stored
-        float4 v0[4], v1[4], v2[4];
-        int cc0 = -1, cc1 = -1, cc2 = -1;
-        load_block(0, v0, cc0);
-        if (p.nkb > 1) load_block(1, v1, cc1);
-        for (int kb = 0; kb < p.nkb; kb += 3) {
-            if (kb + 2 < p.nkb) load_block(kb + 2, v2, cc2);
-            store_block(kb, v0, cc0);
-            if (kb + 1 < p.nkb) {
-                if (kb + 3 < p.nkb) load_block(kb + 3, v0, cc0);
-                store_block(kb + 1, v1, cc1);
-            }
-            if (kb + 2 < p.nkb) {
-                if (kb + 4 < p.nkb) load_block(kb + 4, v1, cc1);
-                store_block(kb + 2, v2, cc2);
-            }
+        float4 v0[RPT], v1[RPT], v2[RPT];
+        int cc0 = 0, cc1 = 0, cc2 = 0;
+        load_next(v0, cc0);
+        load_next(v1, cc1);
+        for (int f = 0; f < total; f += 3) {
+            load_next(v2, cc2);
+            store_item(f, v0, cc0);
+            if (f + 1 < total) { load_next(v0, cc0); store_item(f + 1, v1, cc1); }
+            if (f + 2 < total) { load_next(v1, cc1); store_item(f + 2, v2, cc2); }
         }
-        // ================= epilogue =================
-        mbar_wait(accum_bar, 0u);
-        tc_fence_after();
-        const int q = warp & 3, half = warp >> 2;             // TMEM lane quarter, column half
-        const int row = q * 32 + lane;
-        const int m = m0 + row;
-        const bool mval = m < p.M;
-        size_t opix = 0;
-        if (mval) {
-            int b = m / p.HgWg; int rr = m - b * p.HgWg; int gi = rr / d.Wg; int gj = rr - gi * d.Wg;
-            opix = (size_t)(b * d.Hout + gi * d.osy + d.oy0) * d.Wout + (gj * d.osx + d.ox0);
+        if (p.prof && tid == 0) {
+            long long* o = p.prof + blockIdx.x * 16;
+            o[0] = clock64() - kt0; o[1] = pw_empty; o[2] = pw_load; o[3] = pw_store;
         }
-        float* yp = d.y + opix * d.y_ld;
-        const float rs = (d.row_scale && mval) ? (d.row_scale[m] + d.row_scale_add) : 1.f;
-        const bool vst = (d.Cout % 4 == 0) && (d.y_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15u) == 0);
-        float* red = reinterpret_cast<float*>(sgen);          // [4 quarters][2][BN] floats, stage memory is free now
-        const int nacc = p.nkb < NACC ? p.nkb : NACC;
-        for (int c0 = half * 16; c0 < BN; c0 += 32) {
-            if (n0 + c0 >= d.Cout) break;                     // warp-uniform
-            float v[16];
-            tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            for (int a = 1; a < nacc; ++a) {
-                float u[16];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + c0), u);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += u[j];
-            }
-            float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + c0 + j;
-                const float bj = (d.bias && n < d.Cout) ? __ldg(d.bias + n) : 0.f;
-                v[j] = (mval && n < d.Cout) ? v[j] + bj : 0.f;
-                o[j] = apply_act(v[j] * rs, d.act);
-            }
-            if (mval) {
-                if (vst) {
-#pragma unroll
-                    for (int qq = 0; qq < 4; ++qq) {
-                        const int n = n0 + c0 + 4 * qq;
-                        if (n < d.Cout) {
-                            float4* dst = reinterpret_cast<float4*>(yp + n);
-                            float4 w4 = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
-                            if (d.accumulate) { float4 cur = *dst; w4.x += cur.x; w4.y += cur.y; w4.z += cur.z; w4.w += cur.w; }
-                            *dst = w4;
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + c0 + j;
-                        if (n < d.Cout) yp[n] = d.accumulate ? yp[n] + o[j] : o[j];
-                    }
-                }
-            }
-            if (d.stat_sum) {
-                float sq[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-                const float s1 = colsum16(v, lane);
-                const float s2 = colsum16(sq, lane);
-                if ((lane & 1) == 0) {
-                    red[(q * 2 + 0) * BN + c0 + (lane >> 1)] = s1;
-                    red[(q * 2 + 1) * BN + c0 + (lane >> 1)] = s2;
-                }
-            }
-        }
-        if (d.stat_sum) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int i = tid; i < BN; i += kProducers) {
-                if (n0 + i < d.Cout) {
-                    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) { s1 += red[(w * 2 + 0) * BN + i]; s2 += red[(w * 2 + 1) * BN + i]; }
-                    atomicAdd(d.stat_sum + n0 + i, (double)s1);
-                    atomicAdd(d.stat_sumsq + n0 + i, (double)s2);
-                }
-            }
-        }
-        tc_fence_before();
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
         if (lane == 0) {
             // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int kb = 0; kb < p.nkb; ++kb) {
-                const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
-                mbar_wait(full_a(s), ph);
-                mbar_wait(full_b(s), ph);
+            long long mw_te = 0, mw_fa = 0, mw_fb = 0, mw_issue = 0;
+            int f = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int buf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
+                TC_PROF_T0();
+                mbar_wait(tmem_empty(buf), tph ^ 1u);          // the epilogue has drained this buffer (first use passes)
+                TC_PROF_ADD(mw_te);
                 tc_fence_after();
-                const uint32_t a_hi = sbase + s * Cfg::STAGE;
-                const uint32_t a_lo = a_hi + Cfg::A_BYTES;
-                const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES;
-                const uint32_t b_lo = b_hi + Cfg::B_BYTES;
-                const uint32_t acc = tmem + (uint32_t)((kb % NACC) * Cfg::ACC_COLS);
-                const uint32_t fresh = (kb < NACC) ? 0u : 1u;          // first k-block of each accumulator overwrites
+                for (int kb = 0; kb < nkb; ++kb, ++f) {
+                    const int s = f % NSTAGE; const uint32_t ph = (f / NSTAGE) & 1;
+                    mbar_wait(full_a(s), ph);
+                    TC_PROF_ADD(mw_fa);
+                    mbar_wait(full_b(s), ph);
+                    TC_PROF_ADD(mw_fb);
+                    tc_fence_after();
+                    const uint32_t a_hi = sbase + s * Cfg::STAGE;
+                    const uint32_t a_lo = a_hi + Cfg::A_BYTES;
+                    const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES;
+                    const uint32_t b_lo = b_hi + Cfg::B_BYTES;
+                    const uint32_t acc = tmem + (uint32_t)(buf * Cfg::BUF_COLS + (kb % NACC) * Cfg::ACC_COLS);
+                    const uint32_t fresh = (kb < NACC) ? 0u : 1u;          // first k-block of each accumulator overwrites
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const uint64_t dah = make_desc(a_hi + kk * 32), dbh = make_desc(b_hi + kk * 32);
-                    if (NPASS == 3) {
-                        const uint64_t dal = make_desc(a_lo + kk * 32), dbl = make_desc(b_lo + kk * 32);
-                        mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));       // small terms first
-                        mma_tf32(acc, dah, dbl, idesc, 1u);
-                        mma_tf32(acc, dah, dbh, idesc, 1u);
-                    } else {
-                        mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t dah = make_desc(a_hi + kk * 32), dbh = make_desc(b_hi + kk * 32);
+                        if (NPASS == 3) {
+                            const uint64_t dal = make_desc(a_lo + kk * 32), dbl = make_desc(b_lo + kk * 32);
+                            mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));       // small terms first
+                            mma_tf32(acc, dah, dbl, idesc, 1u);
+                            mma_tf32(acc, dah, dbh, idesc, 1u);
+                        } else {
+                            mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                        }
                     }
+                    mma_commit(empty(s));
+                    TC_PROF_ADD(mw_issue);
                 }
-                mma_commit(empty(s));
+                mma_commit(tmem_full(buf));
             }
-            mma_commit(accum_bar);
+            if (p.prof) {
+                long long* o = p.prof + blockIdx.x * 16;
+                o[4] = mw_te; o[5] = mw_fa; o[6] = mw_fb; o[7] = mw_issue;
+            }
         }
         __syncwarp();
     } else if (warp == LOAD_WARP) {
         // ================= weight-tile loader =================
         if (lane == 0) {
             constexpr uint32_t BYTES = Cfg::NOP * Cfg::B_BYTES;
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wt) + (size_t)blockIdx.y * p.nkb * BYTES;
-            for (int kb = 0; kb < p.nkb; ++kb) {
-                const int s = kb % NSTAGE; const uint32_t ph = (kb / NSTAGE) & 1;
-                mbar_wait(empty(s), ph ^ 1u);
-                mbar_expect_tx(full_b(s), BYTES);
-                bulk_g2s(sbase + s * Cfg::STAGE + Cfg::NOP * Cfg::A_BYTES, src + (size_t)kb * BYTES, BYTES, full_b(s));
+            int f = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+                const int nt = tile % p.ntile_n;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wt) + (size_t)nt * nkb * BYTES;
+                for (int kb = 0; kb < nkb; ++kb, ++f) {
+                    const int s = f % NSTAGE; const uint32_t ph = (f / NSTAGE) & 1;
+                    mbar_wait(empty(s), ph ^ 1u);
+                    mbar_expect_tx(full_b(s), BYTES);
+                    bulk_g2s(sbase + s * Cfg::STAGE + Cfg::NOP * Cfg::A_BYTES, src + (size_t)kb * BYTES, BYTES, full_b(s));
+                }
             }
         }
         __syncwarp();
+    } else {
+        // ================= epilogue =================
+        const int q = warp & 3, half = (warp - EPI_WARP0) >> 2;          // TMEM lane quarter (= warp % 4), column half
+        const int etid = tid - EPI_WARP0 * 32;
+        const int row = q * 32 + lane;
+        const bool vst = (d.Cout % 4 == 0) && (d.y_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15u) == 0);
+        const int nacc = nkb < NACC ? nkb : NACC;
+        long long ew_full = 0, ew_work = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int buf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
+            const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+            const int m0 = (tile / p.ntile_n) * 128, n0 = (tile % p.ntile_n) * BN;
+            const int m = m0 + row;
+            const bool mval = m < p.M;
+            size_t opix = 0;
+            if (mval) {
+                if (MODE == 1) opix = (size_t)m;
+                else {
+                    int b = m / p.HgWg; int rr = m - b * p.HgWg; int gi = rr / d.Wg; int gj = rr - gi * d.Wg;
+                    opix = (size_t)(b * d.Hout + gi * d.osy + d.oy0) * d.Wout + (gj * d.osx + d.ox0);
+                }
+            }
+            float* yp = d.y + opix * d.y_ld;
+            const float rs = (d.row_scale && mval) ? (d.row_scale[m] + d.row_scale_add) : 1.f;
+            TC_PROF_T0();
+            mbar_wait(tmem_full(buf), tph);
+            TC_PROF_ADD(ew_full);
+            tc_fence_after();
+            const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * Cfg::BUF_COLS);
+            for (int c0 = half * 16; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= d.Cout) break;                     // warp-uniform
+                float v[16];
+                tmem_ld16(tb + (uint32_t)c0, v);
+                for (int a = 1; a < nacc; ++a) {
+                    float u[16];
+                    tmem_ld16(tb + (uint32_t)(a * Cfg::ACC_COLS + c0), u);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += u[j];
+                }
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n0 + c0 + j;
+                    const float bj = (d.bias && n < d.Cout) ? __ldg(d.bias + n) : 0.f;
+                    v[j] = (mval && n < d.Cout) ? v[j] + bj : 0.f;
+                    o[j] = apply_act(v[j] * rs, d.act);
+                }
+                if (mval) {
+                    if (vst) {
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const int n = n0 + c0 + 4 * qq;
+                            if (n < d.Cout) {
+                                float4* dst = reinterpret_cast<float4*>(yp + n);
+                                float4 w4 = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
+                                if (d.accumulate) { float4 cur = *dst; w4.x += cur.x; w4.y += cur.y; w4.z += cur.z; w4.w += cur.w; }
+                                *dst = w4;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int n = n0 + c0 + j;
+                            if (n < d.Cout) yp[n] = d.accumulate ? yp[n] + o[j] : o[j];
+                        }
+                    }
+                }
+                if (d.stat_sum) {
+                    float sq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                    const float s1 = colsum16(v, lane);
+                    const float s2 = colsum16(sq, lane);
+                    if ((lane & 1) == 0) {
+                        red[(q * 2 + 0) * BN + c0 + (lane >> 1)] = s1;
+                        red[(q * 2 + 1) * BN + c0 + (lane >> 1)] = s2;
+                    }
+                }
+            }
+            // the accumulator buffer is free as soon as every epilogue warp has read it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(buf));
+            if (d.stat_sum) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                for (int i = etid; i < BN; i += kEpilogue) {
+                    if (n0 + i < d.Cout) {
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) { s1 += red[(w * 2 + 0) * BN + i]; s2 += red[(w * 2 + 1) * BN + i]; }
+                        atomicAdd(d.stat_sum + n0 + i, (double)s1);
+                        atomicAdd(d.stat_sumsq + n0 + i, (double)s2);
+                    }
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // red is rewritten by the next tile
+            }
+            TC_PROF_ADD(ew_work);
+        }
+        if (p.prof && etid == 0) {
+            long long* o = p.prof + blockIdx.x * 16;
+            o[8] = ew_full; o[9] = ew_work;
+        }
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
@@ -328,19 +426,32 @@ __global__ void pack_tc_kernel(const float* __restrict__ kn, int K, int N, int B
     }
 }
 
-template <int BN, int NPASS>
-static int launch_tc(const TcP& p, cudaStream_t st) {
+template <int BN, int NPASS, int MODE>
+static int launch_tc_mode(const TcP& p, cudaStream_t st) {
     using Cfg = TcCfg<BN, NPASS>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, NPASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, NPASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
         if (e != cudaSuccess) { set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return SAUNET_ERR_CUDA; }
         attr_set = true;
     }
-    dim3 grid(cdiv(p.M, 128), cdiv(p.d.Cout, BN));
-    conv_tc_kernel<BN, NPASS><<<grid, kTcThreads, Cfg::SMEM, st>>>(p);
+    TcP q = p;
+    q.ntile_n = cdiv(p.d.Cout, BN);
+    q.ntiles = cdiv(p.M, 128) * q.ntile_n;
+    const char* pe = getenv("SAUNET_TC_PROF");          // debugging aid: device pointer to long long[148][16]
+    q.prof = pe ? reinterpret_cast<long long*>(strtoull(pe, nullptr, 0)) : nullptr;
+    const int grid = q.ntiles < kNumSMs ? q.ntiles : kNumSMs;
+    conv_tc_kernel<BN, NPASS, MODE><<<grid, kTcThreads, Cfg::SMEM, st>>>(q);
     SAUNET_CHECK_LAUNCH("conv_tc_kernel");
     return SAUNET_OK;
+}
+template <int BN, int NPASS>
+static int launch_tc(const TcP& p, cudaStream_t st) {
+    const saunet_conv_desc& d = p.d;
+    if (d.KH == 1 && d.KW == 1 && d.sy == 1 && d.sx == 1 && d.offy == 0 && d.offx == 0 && d.Hg == d.Hin && d.Wg == d.Win)
+        return launch_tc_mode<BN, NPASS, 1>(p, st);
+    if (p.chunk_major) return launch_tc_mode<BN, NPASS, 2>(p, st);
+    return launch_tc_mode<BN, NPASS, 0>(p, st);
 }
 
 bool conv_tc_eligible(const saunet_conv_desc* d) {

@@ -22,15 +22,24 @@ dw = torch.zeros(k * k * Cin * Cout, device=dev)
 def run():
     if kind == "fwd":
         conv(tp, x, packed(tp, w, 0), Cout, k, k, y, H, W, offy=-(k // 2), offx=-(k // 2),
-             stat=(st.data_ptr(), st.data_ptr() + 8 * Cout), wtc=packed_tc(tp, w, 0, k * k, Cin, Cout))
+             stat=None if os.environ.get('NOSTAT') else (st.data_ptr(), st.data_ptr() + 8 * Cout), wtc=packed_tc(tp, w, 0, k * k, Cin, Cout))
     else:
         wgrad(tp, y, x, dw.data_ptr(), k, k, H, W, offy=-(k // 2), offx=-(k // 2))
 for _ in range(2): run()
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(iters): run()
-e1.record(); torch.cuda.synchronize()
+# time a CUDA graph of `iters` launches: the Python/ctypes launch path (~50-100 us per call) must not be what is measured
+side = torch.cuda.Stream()
+with torch.cuda.stream(side):
+    tp.stream = side.cuda_stream
+    run(); side.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(iters): run()
+    graph.replay(); side.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(side)
+    graph.replay()
+    e1.record(side); side.synchronize()
 ms = e0.elapsed_time(e1) / iters
 fl = 2.0 * B * H * W * k * k * Cin * Cout
 print("%s B%d %dx%d %d->%d k%d: %.3f ms  %.1f TFLOP/s" % (kind, B, H, W, Cin, Cout, k, ms, fl / ms / 1e9))
