@@ -178,13 +178,7 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
                 for (int j = 0; j < 16; ++j) v[j] += u[j];
             }
             float o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + c0 + j;
-                const float bj = (d.bias && n < d.Cout) ? __ldg(d.bias + n) : 0.f;
-                v[j] = (n < d.Cout) ? v[j] + bj : 0.f;
-                o[j] = apply_act(v[j] * rs, d.act);
-            }
+            epi_chunk(v, o, d.bias ? d.bias + n0 + c0 : nullptr, d.Cout - (n0 + c0), true, true, d.row_scale != nullptr, rs, d.act);
             if (vst) {
 #pragma unroll
                 for (int qq = 0; qq < 4; ++qq) {

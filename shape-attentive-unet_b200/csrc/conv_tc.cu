@@ -44,10 +44,15 @@ struct TcCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int NOP = (NPASS == 3) ? 2 : 1;                 // hi (+ lo) images per operand
     static constexpr int STAGE = NOP * (A_BYTES + B_BYTES);
-    static constexpr int NSTAGE_RAW = (196 * 1024) / STAGE;
-    static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : (NSTAGE_RAW < 2 ? 2 : NSTAGE_RAW);
     static constexpr int RED_BYTES = 8 * BN * 4;                     // [4 lane quarters][sum, sumsq][BN] floats
-    static constexpr int SMEM = NSTAGE * STAGE + RED_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // output staging tile for the bulk-copy epilogue: 128 rows of BN floats at a pitch of BN*4 + 16 bytes (the 16 bytes
+    // of padding make the row-per-thread 128-bit stores conflict-free)
+    static constexpr int OUT_PITCH = BN * 4 + 16;
+    static constexpr int OUT_BYTES = 128 * OUT_PITCH;
+    static constexpr int NSTAGE_RAW = (227 * 1024 - 1024 - 256 - RED_BYTES - OUT_BYTES) / STAGE;
+    static constexpr int NSTAGE = NSTAGE_RAW > 4 ? 4 : NSTAGE_RAW;
+    static_assert(NSTAGE >= 2, "shared memory: two pipeline stages must fit");
+    static constexpr int SMEM = NSTAGE * STAGE + OUT_BYTES + RED_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     static constexpr int NBUF = 2;                                   // accumulator buffers (epilogue overlap)
     // The tensor core rounds its fp32 accumulator toward zero on every MMA, a bias that grows linearly with K
@@ -77,14 +82,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-    float* red = reinterpret_cast<float*>(sgen + NSTAGE * Cfg::STAGE);
-    const uint32_t bars = sbase + NSTAGE * Cfg::STAGE + Cfg::RED_BYTES;
+    uint8_t* ostage = sgen + NSTAGE * Cfg::STAGE;
+    float* red = reinterpret_cast<float*>(ostage + Cfg::OUT_BYTES);
+    const uint32_t bars = sbase + NSTAGE * Cfg::STAGE + Cfg::OUT_BYTES + Cfg::RED_BYTES;
     auto full_a = [&](int s) { return bars + 8u * s; };
     auto full_b = [&](int s) { return bars + 8u * (NSTAGE + s); };
     auto empty = [&](int s) { return bars + 8u * (2 * NSTAGE + s); };
     auto tmem_full = [&](int b) { return bars + 8u * (3 * NSTAGE + b); };
     auto tmem_empty = [&](int b) { return bars + 8u * (3 * NSTAGE + 2 + b); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + NSTAGE * Cfg::STAGE + Cfg::RED_BYTES + 8 * (3 * NSTAGE + 4));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + NSTAGE * Cfg::STAGE + Cfg::OUT_BYTES + Cfg::RED_BYTES + 8 * (3 * NSTAGE + 4));
 
     const saunet_conv_desc& d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -292,15 +298,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const int q = warp & 3, half = (warp - EPI_WARP0) >> 2;          // TMEM lane quarter (= warp % 4), column half
         const int etid = tid - EPI_WARP0 * 32;
         const int row = q * 32 + lane;
+        // vst: rows are 16-byte aligned -> the tile is staged in shared memory and written (or added, for accumulating
+        // data gradients) one whole row per cp.async.bulk: a warp-wide "row per thread" store touches 32 different
+        // rows and halves the SM->L2 write rate (the epilogue then bounds every short-K tile)
         const bool vst = (d.Cout % 4 == 0) && (d.y_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15u) == 0);
         const int nacc = nkb < NACC ? nkb : NACC;
-        long long ew_full = 0, ew_work = 0;
+        long long ew_full = 0, ew_work = 0, ew_ld = 0, ew_alu = 0, ew_bar = 0;
+        uint8_t* orow = ostage + (size_t)row * Cfg::OUT_PITCH;
         for (int ti = 0; ti < my_tiles; ++ti) {
+            if (ti > 0) {
+                // the previous tile's bulk copies have finished reading the staging tile; red[] has been consumed
+                if (vst) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             const int buf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
             const int m0 = (tile / p.ntile_n) * 128, n0 = (tile % p.ntile_n) * BN;
             const int m = m0 + row;
             const bool mval = m < p.M;
+            const bool tile_full = m0 + 128 <= p.M;
             size_t opix = 0;
             if (mval) {
                 if (MODE == 1) opix = (size_t)m;
@@ -319,6 +335,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             for (int c0 = half * 16; c0 < BN; c0 += 32) {
                 if (n0 + c0 >= d.Cout) break;                     // warp-uniform
                 float v[16];
+                long long pq0 = p.prof ? clock64() : 0;
                 tmem_ld16(tb + (uint32_t)c0, v);
                 for (int a = 1; a < nacc; ++a) {
                     float u[16];
@@ -326,27 +343,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += u[j];
                 }
+                if (p.prof) { long long t = clock64(); ew_ld += t - pq0; pq0 = t; }
                 float o[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n0 + c0 + j;
-                    const float bj = (d.bias && n < d.Cout) ? __ldg(d.bias + n) : 0.f;
-                    v[j] = (mval && n < d.Cout) ? v[j] + bj : 0.f;
-                    o[j] = apply_act(v[j] * rs, d.act);
+                {
+                    const int nvalid = d.Cout - (n0 + c0);
+                    epi_chunk(v, o, d.bias ? d.bias + n0 + c0 : nullptr, nvalid, tile_full, mval, d.row_scale != nullptr, rs, d.act);
                 }
-                if (mval) {
-                    if (vst) {
+                if (vst) {
 #pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            const int n = n0 + c0 + 4 * qq;
-                            if (n < d.Cout) {
-                                float4* dst = reinterpret_cast<float4*>(yp + n);
-                                float4 w4 = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
-                                if (d.accumulate) { float4 cur = *dst; w4.x += cur.x; w4.y += cur.y; w4.z += cur.z; w4.w += cur.w; }
-                                *dst = w4;
-                            }
-                        }
-                    } else {
+                    for (int qq = 0; qq < 4; ++qq)
+                        *reinterpret_cast<float4*>(orow + (c0 + 4 * qq) * 4) = make_float4(o[4 * qq], o[4 * qq + 1], o[4 * qq + 2], o[4 * qq + 3]);
+                } else if (mval) {
+                    {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             const int n = n0 + c0 + j;
@@ -354,6 +362,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                         }
                     }
                 }
+                if (p.prof) { long long t = clock64(); ew_alu += t - pq0; pq0 = t; }
                 if (d.stat_sum) {
                     float sq[16];
 #pragma unroll
@@ -370,8 +379,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty(buf));
+            long long pq1 = p.prof ? clock64() : 0;
+            if (vst) fence_proxy_async();                  // staging-tile stores -> visible to the bulk-copy engine
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (p.prof) ew_bar += clock64() - pq1;
+            if (vst && etid < 128 && mval) {               // thread etid < 128 owns row etid (== row)
+                const int ncols = (d.Cout - n0) < BN ? (d.Cout - n0) : BN;
+                const uint32_t src = smem_u32(orow);
+                float* dst = yp + n0;
+                if (d.accumulate)
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(ncols * 4) : "memory");
+                else
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(ncols * 4) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
             if (d.stat_sum) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
                 for (int i = etid; i < BN; i += kEpilogue) {
                     if (n0 + i < d.Cout) {
                         float s1 = 0.f, s2 = 0.f;
@@ -381,13 +403,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                         atomicAdd(d.stat_sumsq + n0 + i, (double)s2);
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");      // red is rewritten by the next tile
             }
             TC_PROF_ADD(ew_work);
         }
+        if (vst) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         if (p.prof && etid == 0) {
             long long* o = p.prof + blockIdx.x * 16;
-            o[8] = ew_full; o[9] = ew_work;
+            o[8] = ew_full; o[9] = ew_work; o[10] = ew_ld; o[11] = ew_alu; o[12] = ew_bar;
         }
     }
     tc_fence_before();
@@ -475,7 +497,6 @@ int conv_fwd_tc(const saunet_conv_desc* d, cudaStream_t st) {
         case 32: return three ? launch_tc<32, 3>(p, st) : launch_tc<32, 1>(p, st);
         case 64: return three ? launch_tc<64, 3>(p, st) : launch_tc<64, 1>(p, st);
         case 128: return three ? launch_tc<128, 3>(p, st) : launch_tc<128, 1>(p, st);
-        case 256: return three ? launch_tc<256, 3>(p, st) : launch_tc<256, 1>(p, st);
     }
     set_error("conv2d_fwd(tc): unsupported N tile %d", d->tc_bn);
     return SAUNET_ERR_BAD_SHAPE;
@@ -490,8 +511,7 @@ extern "C" int saunet_tc_tile_n(int Cout) {
     if (Cout <= 16) return 16;
     if (Cout <= 32) return 32;
     if (Cout <= 64) return 64;
-    if (Cout <= 128) return 128;
-    return 256;
+    return 128;        // (a 256-wide tile leaves no shared memory for the output staging tile of the bulk-copy epilogue)
 }
 extern "C" long long saunet_tc_packed_floats(int K, int N, int BN, int passes) {
     if (K <= 0 || N <= 0 || BN <= 0) return 0;
@@ -501,7 +521,7 @@ extern "C" long long saunet_tc_packed_floats(int K, int N, int BN, int passes) {
 extern "C" int saunet_pack_weights_tc(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream) {
     const int K = taps * Cin;
     SAUNET_CHECK_ARG(kn && out && taps > 0 && Cin > 0 && N > 0, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: bad args");
-    SAUNET_CHECK_ARG(BN == 16 || BN == 32 || BN == 64 || BN == 128 || BN == 256, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: bad N tile %d", BN);
+    SAUNET_CHECK_ARG(BN == 16 || BN == 32 || BN == 64 || BN == 128, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: bad N tile %d", BN);
     SAUNET_CHECK_ARG(passes == 1 || passes == 3, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: passes must be 1 or 3");
     const long long total = saunet_tc_packed_floats(K, N, BN, passes);
     int blocks = (int)((total + 255) / 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;

@@ -90,6 +90,46 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
+// epilogue math on one 16-column chunk of a row: v = acc + bias (exactly 0 for rows / columns outside the problem, so
+// that the BatchNorm statistics see nothing), o = act(v * rs).  Every branch is warp-uniform except the row mask.
+__device__ __forceinline__ void epi_chunk(float (&v)[16], float (&o)[16], const float* bias, int nvalid, bool tile_full,
+                                          bool mval, bool has_rs, float rs, int act) {
+    if (bias) {
+        if (nvalid >= 16 && ((reinterpret_cast<uintptr_t>(bias) & 15u) == 0)) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q4);
+                v[4 * q4] += b.x; v[4 * q4 + 1] += b.y; v[4 * q4 + 2] += b.z; v[4 * q4 + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j < nvalid) v[j] += __ldg(bias + j);
+        }
+    }
+    if (nvalid < 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (j >= nvalid) v[j] = 0.f;
+    }
+    if (!tile_full) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = mval ? v[j] : 0.f;
+    }
+    if (has_rs) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = v[j] * rs;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = v[j];
+    }
+    if (act == SAUNET_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+    } else if (act == SAUNET_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = sigmoid_acc(o[j]);
+    }
+}
+
 // column sums of a [32 lanes][16 cols] register tile by transpose-reduce: 16 shuffles instead of 80.
 // afterwards lane L holds the sum of column (L >> 1).
 __device__ __forceinline__ float colsum16(float (&v)[16], int lane) {

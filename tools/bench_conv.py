@@ -42,4 +42,17 @@ with torch.cuda.stream(side):
     e1.record(side); side.synchronize()
 ms = e0.elapsed_time(e1) / iters
 fl = 2.0 * B * H * W * k * k * Cin * Cout
+if os.environ.get("PROF") and kind == "fwd":
+    prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    os.environ["SAUNET_TC_PROF"] = str(prof.data_ptr())
+    tp.stream = torch.cuda.current_stream().cuda_stream
+    run(); torch.cuda.synchronize()
+    del os.environ["SAUNET_TC_PROF"]
+    pr = prof.view(148, 16).double().cpu()
+    pr = pr[pr[:, 0] > 0]
+    names = ["total", "prod:wait_empty", "prod:transform(+load latency)", "prod:fence+arrive", "mma:wait_tmem_empty", "mma:wait_full_a",
+             "mma:wait_full_b", "mma:issue+commit", "epi:wait_tmem_full", "epi:work", "epi:tmem_ld", "epi:alu+st", "epi:fence+bar"]
+    tot = float(pr[:, 0].mean())
+    print("  per-role cycles (mean over %d CTAs, kernel = %.0f cycles): " % (pr.shape[0], tot) +
+          ", ".join("%s %.0f%%" % (n, 100 * float(pr[:, i].mean()) / tot) for i, n in enumerate(names) if i))
 print("%s B%d %dx%d %d->%d k%d: %.3f ms  %.1f TFLOP/s" % (kind, B, H, W, Cin, Cout, k, ms, fl / ms / 1e9))
