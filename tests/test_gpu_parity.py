@@ -239,7 +239,9 @@ def test_saunet_train_step_vs_reference(tag, batch, size, precision):
     nf = 10.0
     for k, ref in zip(names, g["grad_l2"]):
         got = float(params[k].grad.double().norm())
-        if _is_zero_bias(k):
+        if _is_zero_bias(k) or float(ref) < 1e-5:
+            # mathematically zero gradients (a bias in front of a train-mode BatchNorm, e.g. norm0.bias): both sides
+            # hold rounding noise only (reference ~2e-7), whose ratio means nothing
             assert got < 1e-3 and float(ref) < 1e-3, k
             continue
         err = abs(got - float(ref)) / max(float(ref), 1e-12)
