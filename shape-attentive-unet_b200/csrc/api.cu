@@ -25,6 +25,8 @@ int conv_wgrad_tc(const saunet_wgrad_desc* d, cudaStream_t st);
 bool conv_wgrad_tc_eligible(const saunet_wgrad_desc* d);
 int conv_wgrad_halo(const saunet_wgrad_desc* d, cudaStream_t st);
 bool conv_wgrad_halo_eligible(const saunet_wgrad_desc* d);
+int conv_wgrad_pw(const saunet_wgrad_desc* d, cudaStream_t st);
+bool conv_wgrad_pw_eligible(const saunet_wgrad_desc* d);
 }  // namespace saunet
 
 using namespace saunet;
@@ -56,6 +58,7 @@ extern "C" int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream) {
                      d->Wg > 0 && d->sy > 0 && d->sx > 0, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: non-positive dimension");
     SAUNET_CHECK_ARG(d->p_ld >= d->Ca && d->q_ld >= d->Cb, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: ld smaller than channel count");
     SAUNET_CHECK_ARG((d->q_scale == nullptr) == (d->q_shift == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: q_scale/q_shift mismatch");
+    if (conv_wgrad_pw_eligible(d) && !getenv("SAUNET_NO_WGRAD_PW")) return conv_wgrad_pw(d, (cudaStream_t)stream);
     if (conv_wgrad_skinny_eligible(d)) return conv_wgrad_skinny(d, (cudaStream_t)stream);
     if (conv_wgrad_halo_eligible(d) && !getenv("SAUNET_NO_WGRAD_HALO")) return conv_wgrad_halo(d, (cudaStream_t)stream);
     if (conv_wgrad_tc_eligible(d)) return conv_wgrad_tc(d, (cudaStream_t)stream);

@@ -114,6 +114,13 @@ WG_CASES = [
     (2, 8, 8, 512, 256, 3, 1, -1, False, 0, 0),       # several M / N tiles
     (3, 24, 24, 16, 8, 1, 1, 0, False, 0, 0),         # tiny channel counts
     (2, 6, 5, 64, 32, 4, 2, -1, False, 0, 0),         # conv-transpose wgrad: P = x (low-res), Q = dY gathered at stride 2
+    # pointwise convs -> conv_wgrad_pw.cu (dY on the 128 TMEM lanes, up to 512 Q channels per CTA)
+    (2, 32, 32, 128, 224, 1, 1, 0, True, 0, 32),      # dense conv1, Q = first 224 channels of a 256-wide concat buffer
+    (1, 16, 16, 128, 992, 1, 1, 0, True, 0, 32),      # deepest dense layer: two Q tiles of 496 channels
+    (2, 24, 24, 256, 512, 1, 1, 0, True, 0, 0),       # transition: two dY tiles
+    (1, 40, 40, 32, 64, 1, 1, 0, False, 0, 0),        # shape stream d1
+    (3, 9, 7, 48, 40, 1, 1, 0, False, 16, 8),         # ragged pixel count (189 pixels), partial planes on both sides
+    (2, 64, 64, 8, 32, 1, 1, 0, False, 0, 0),         # tiny dY
     (2, 16, 16, 64, 4, 7, 2, -3, False, 0, 0),        # the 7x7 / stride 2 stem on its 4-channel padded input
     # 3x3 / s1 / p1 with H % 8 == 0, W % 8 == 0, Ca <= 64 -> the all-taps halo kernel (conv_wgrad_halo.cu)
     (2, 16, 24, 32, 128, 3, 1, -1, True, 96, 0),      # dense conv2: dY is a slice of the concat-buffer gradient
