@@ -45,7 +45,12 @@ struct HaloCfg {
     static constexpr int NSTB_RAW = B_SPACE / B_STAGE;
     static constexpr int NSTB = NSTB_RAW > 4 ? 4 : NSTB_RAW;
     static constexpr int SMEM = NBUF * PATCH + NSTB * B_STAGE + 1024 + 256;
-    static constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    // Narrow tiles are bound by the tensor core's operand reads from shared memory (the 128x32 fp32 A tile of every MMA
+    // is 4 KB whatever N is), not by its math: for BN <= 64 the hi and lo weight images, adjacent in the stage, are fed
+    // as ONE N = 2*BN operand, so A_hi is read once for the hi*hi and hi*lo products (2 MMAs per K step instead of 3);
+    // the two halves accumulate in separate TMEM columns and are added in the epilogue.
+    static constexpr bool CAT = (NPASS == 3) && (BN <= 64);
+    static constexpr int ACC_COLS = (BN < 32 ? 32 : BN) * (CAT ? 2 : 1);
     static constexpr int NACC = (256 / ACC_COLS) > 4 ? 4 : (256 / ACC_COLS);
     static constexpr int TMEM_COLS = NACC * ACC_COLS;
     static_assert(NSTB >= 2, "weight ring needs two stages");
@@ -171,11 +176,18 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
             if (n0 + c0 >= d.Cout) break;
             float v[16];
             tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            for (int a = 1; a < nacc; ++a) {
+            for (int a = 0; a < nacc; ++a) {
                 float u[16];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + c0), u);
+                if (a > 0) {
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + c0), u);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] += u[j];
+                    for (int j = 0; j < 16; ++j) v[j] += u[j];
+                }
+                if (Cfg::CAT) {                               // the hi*lo + lo*hi half of the accumulator
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * Cfg::ACC_COLS + BN + c0), u);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += u[j];
+                }
             }
             float o[16];
             epi_chunk(v, o, d.bias ? d.bias + n0 + c0 : nullptr, d.Cout - (n0 + c0), true, true, d.row_scale != nullptr, rs, d.act);
@@ -225,6 +237,7 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int kb = 0;
             for (int cc = 0; cc < p.nchunk; ++cc) {
                 const int buf = cc % Cfg::NBUF; const uint32_t pph = (cc / Cfg::NBUF) & 1;
@@ -244,7 +257,11 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
                         const uint64_t dah = make_desc_sbo(a_hi0 + shift + kk * 32, kPitch * 128), dbh = make_desc(b_hi + kk * 32);
-                        if (NPASS == 3) {
+                        if (Cfg::CAT) {
+                            const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kPitch * 128);
+                            mma_tf32(acc, dah, dbh, idesc2, (kk ? 1u : fresh));       // [hi*hi | hi*lo]: B rows BN..2BN-1 are the lo image
+                            mma_tf32(acc + BN, dal, dbh, idesc, 1u);                  // lo*hi joins the small-terms half
+                        } else if (NPASS == 3) {
                             const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kPitch * 128), dbl = make_desc(b_lo + kk * 32);
                             mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));
                             mma_tf32(acc, dah, dbl, idesc, 1u);

@@ -235,7 +235,9 @@ def test_saunet_train_step_vs_reference(tag, batch, size, precision):
     names = [str(n) for n in g["grad_names"]]
     assert set(names) == {k for k, p in params.items() if p.grad is not None}
     # exact fp32: 10x the 1-ulp (1e-7) noise; 3xTF32 rounds every product at ~2^-21 (about 10 ulp): 10x the 1e-6 noise
-    noise = _grad_noise(batch, size, 1e-7 if precision == "fp32" else 1e-6)
+    # (fp32 path: atomically accumulated statistics / weight gradients make the summation order, hence the last few
+    #  ulps, vary from run to run: its floor is the 3-ulp noise)
+    noise = _grad_noise(batch, size, 3e-7 if precision == "fp32" else 1e-6)
     nf = 10.0
     for k, ref in zip(names, g["grad_l2"]):
         got = float(params[k].grad.double().norm())
