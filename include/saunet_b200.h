@@ -103,6 +103,16 @@ long long saunet_tc_packed_floats(int K, int N, int BN, int passes);
 int saunet_tc_chunk_major(int taps, int Cin);   /* 1: K-blocks ordered (32-channel chunk, tap) for L1 reuse across taps */
 int saunet_pack_weights_tc(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream);
 int saunet_unpack_wgrad(const float* packed, float* wgrad, int A, int Bc, int KH, int KW, int accumulate, void* stream);
+/* the same for every conv weight of a model in one launch (flat gradient arena, saunet_b200.parallel.GradArena):
+ * grad_base[grad_off + ((a*Bc + b)*T + t)] += packed_base[packed_off + ((t*Bc + b)*A + a)], then that packed
+ * element is reset to 0 (the images stay all-zero between backward passes); table lives in device
+ * memory, `first` = exclusive prefix sum of A*Bc*T over the entries, total = their sum. */
+typedef struct saunet_unpack_entry {
+    long long first, packed_off, grad_off;
+    int A, Bc, T, pad_;
+} saunet_unpack_entry;
+int saunet_unpack_wgrad_multi(const saunet_unpack_entry* table, int n, long long total, float* packed_base,
+                              float* grad_base, void* stream);   /* (clears every packed element it consumes) */
 
 /* ---- batch norm (nn.BatchNorm2d / SynchronizedBatchNorm2d outside DataParallel == F.batch_norm;
  *      lib/nn/modules/batchnorm.py:58-61; Appendix A of SURVEY.md) ---------------------------------- */

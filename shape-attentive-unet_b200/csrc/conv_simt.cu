@@ -504,9 +504,35 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
     }
 }
 
+// all conv weight gradients of a model in ONE launch: entry j describes parameter j (packed [(t,b)][a] image at
+// packed_base + packed_off, parameter-layout gradient w[a][b][t] at grad_base + grad_off); `first` = prefix sum of
+// element counts.  Thread -> flat element index -> binary search for its parameter.
+__global__ void unpack_wgrad_multi_kernel(const saunet_unpack_entry* __restrict__ tab, int n, long long total,
+                                          float* __restrict__ packed_base, float* __restrict__ grad_base) {
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tab[mid].first <= idx) lo = mid; else hi = mid - 1; }
+        const saunet_unpack_entry e = tab[lo];
+        const long long loc = idx - e.first;
+        const int t = (int)(loc % e.T); const long long r = loc / e.T; const int b = (int)(r % e.Bc); const int a = (int)(r / e.Bc);
+        float* src = packed_base + e.packed_off + ((size_t)t * e.Bc + b) * e.A + a;
+        grad_base[e.grad_off + loc] += *src;
+        *src = 0.f;                                    // consumed: the image is all-zero again for the next backward
+    }
+}
+
 }  // namespace saunet
 
 using namespace saunet;
+
+extern "C" int saunet_unpack_wgrad_multi(const saunet_unpack_entry* table, int n, long long total, float* packed_base,
+                                         float* grad_base, void* stream) {
+    SAUNET_CHECK_ARG(table && packed_base && grad_base && n > 0 && total > 0, SAUNET_ERR_BAD_SHAPE, "unpack_wgrad_multi: bad args");
+    long long blocks = (total + 255) / 256; if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    unpack_wgrad_multi_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(table, n, total, packed_base, grad_base);
+    SAUNET_CHECK_LAUNCH("unpack_wgrad_multi_kernel");
+    return SAUNET_OK;
+}
 
 extern "C" int saunet_pack_weights(const float* w, float* packed, int A, int Bc, int KH, int KW, int mode, void* stream) {
     SAUNET_CHECK_ARG(w && packed && A > 0 && Bc > 0 && KH > 0 && KW > 0, SAUNET_ERR_BAD_SHAPE, "pack_weights: bad args");

@@ -33,6 +33,11 @@ class WgradDesc(Structure):
                 ("q_scale", c_void_p), ("q_shift", c_void_p), ("q_relu", c_int), ("dw", c_void_p), ("precision", c_int)]
 
 
+class UnpackEntry(Structure):
+    _fields_ = [("first", c_longlong), ("packed_off", c_longlong), ("grad_off", c_longlong),
+                ("A", c_int), ("Bc", c_int), ("T", c_int), ("pad_", c_int)]
+
+
 _P, _I, _L, _F, _D = c_void_p, c_int, c_longlong, c_float, c_double
 
 # name -> argtypes (restype is int unless listed in _SPECIAL)
@@ -41,6 +46,7 @@ SIGNATURES = {
     "saunet_conv2d_wgrad": [POINTER(WgradDesc), _P],
     "saunet_pack_weights": [_P, _P, _I, _I, _I, _I, _I, _P],
     "saunet_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "saunet_unpack_wgrad_multi": [_P, _I, _L, _P, _P, _P],
     "saunet_pack_weights_tc": [_P, _I, _I, _I, _I, _I, _P, _P],
     "saunet_channel_stats": [_P, _I, _I, _L, _P, _P, _P],
     "saunet_add_d2f": [_P, _P, _I, _P],

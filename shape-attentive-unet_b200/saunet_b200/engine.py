@@ -86,6 +86,7 @@ class Tape:
         self._keep = []
         self.bn_tracked = []
         self.arena = None
+        self.used_packed = False
         self.repacked = []      # pack-cache entries refreshed under FORCE_PACK by this tape (flag reset at the end)
 
     # ---- memory ---------------------------------------------------------
@@ -161,10 +162,23 @@ class Tape:
             self.pgrads[p] = g
         return g.data_ptr()
 
+    def packed_grad(self, p):
+        """Packed weight-gradient target of conv weight ``p`` inside the attached GradArena (zeroed with the arena,
+        unpacked once at the end of backward), or None -> per-conv temporary + unpack launch."""
+        if self.arena is not None:
+            ptr = self.arena.packed_ptr(p)
+            if ptr is not None:
+                self.used_packed = True
+                return ptr
+        return None
+
     def backward(self):
         for fn in reversed(self.ops):
             fn()
         self.ops = []
+        if self.used_packed:
+            self.arena.unpack(self.stream)
+            self.used_packed = False
 
     def on_backward(self, fn):
         if self.record:
@@ -413,10 +427,12 @@ def conv2d_bwd(tp, r, dy, dx=None, dx_acc=0, need_bias=True):
     w, x = r.w, r.x
     Cout, Cin, KH, KW = w.shape
     if w.requires_grad:
-        dwp = torch.zeros(w.numel(), dtype=torch.float32, device=tp.device)
-        wgrad(tp, dy, x, dwp.data_ptr(), KH, KW, dy.H, dy.W, sy=r.stride, sx=r.stride, offy=-r.pad, offx=-r.pad,
+        pk = tp.packed_grad(w)
+        dwp = None if pk else torch.zeros(w.numel(), dtype=torch.float32, device=tp.device)
+        wgrad(tp, dy, x, pk or dwp.data_ptr(), KH, KW, dy.H, dy.W, sy=r.stride, sx=r.stride, offy=-r.pad, offx=-r.pad,
               pro=r.pro.state if r.pro is not None else 0, pro_relu=r.pro_relu)
-        _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cout, Cin, KH, KW, 1, tp.stream)
+        if not pk:
+            _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cout, Cin, KH, KW, 1, tp.stream)
     if r.b is not None and r.b.requires_grad and need_bias:
         bias_grad(tp, dy, r.b)
     if dx is not None:
@@ -444,9 +460,11 @@ def convT4(tp, x, w, b, y, stat=None):
 def convT4_bwd(tp, x, w, b, dy, dx, dx_acc):
     Cin, Cout, _, _ = w.shape
     if w.requires_grad:
-        dwp = torch.zeros(w.numel(), dtype=torch.float32, device=tp.device)
-        wgrad(tp, x, dy, dwp.data_ptr(), 4, 4, x.H, x.W, sy=2, sx=2, offy=-1, offx=-1)
-        _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cin, Cout, 4, 4, 1, tp.stream)
+        pk = tp.packed_grad(w)
+        dwp = None if pk else torch.zeros(w.numel(), dtype=torch.float32, device=tp.device)
+        wgrad(tp, x, dy, pk or dwp.data_ptr(), 4, 4, x.H, x.W, sy=2, sx=2, offy=-1, offx=-1)
+        if not pk:
+            _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cin, Cout, 4, 4, 1, tp.stream)
     if b is not None and b.requires_grad:
         bias_grad(tp, dy, b)
     if dx is not None:

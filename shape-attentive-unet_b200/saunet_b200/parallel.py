@@ -30,20 +30,57 @@ class GradArena:
         for p in params:
             self.offsets[id(p)] = off
             off += (p.numel() + 3) // 4 * 4          # keep every view 16-byte aligned
-        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        # second half of the allocation: the conv kernels' PACKED weight-gradient images ([(tap, cin)][cout], what the
+        # tensor-core wgrad epilogues write with coalesced atomics); one table-driven kernel folds all of them into the
+        # parameter-layout gradients at the end of backward (instead of a zero-fill + an unpack launch per conv)
+        self.n_grad = off
+        self.packed_off = {}
+        entries, first = [], 0
+        for p in params:
+            if p.dim() == 4:
+                self.packed_off[id(p)] = off
+                a, b, kh, kw = p.shape
+                entries.append((first, off - self.n_grad, self.offsets[id(p)], a, b, kh * kw))
+                first += p.numel()
+                off += (p.numel() + 3) // 4 * 4
+        self.flat_all = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.flat = self.flat_all[:self.n_grad]
+        self.packed = self.flat_all[self.n_grad:]
+        self._unpack_total = first
+        self._unpack_n = len(entries)
+        if entries:
+            import ctypes
+            from . import _C
+            arr = (_C.UnpackEntry * len(entries))()
+            for i, e in enumerate(entries):
+                arr[i].first, arr[i].packed_off, arr[i].grad_off, arr[i].A, arr[i].Bc, arr[i].T = e
+            raw = bytes(arr)
+            self._unpack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         for p in params:
             o = self.offsets[id(p)]
             p.grad = self.flat[o:o + p.numel()].view_as(p)
         n = max(1, int(bucket_mb * (1 << 20) // 4))
-        self.buckets = [self.flat[i:i + n] for i in range(0, off, n)]
+        self.buckets = [self.flat[i:i + n] for i in range(0, self.n_grad, n)]
         module._saunet_grad_arena = self
 
     def ptr(self, p):
         o = self.offsets.get(id(p))
         return None if o is None else self.flat.data_ptr() + 4 * o
 
+    def packed_ptr(self, p):
+        """Device pointer of the packed weight-gradient image of conv weight ``p`` (None: not a conv weight here)."""
+        o = self.packed_off.get(id(p))
+        return None if o is None else self.flat_all.data_ptr() + 4 * o
+
+    def unpack(self, stream):
+        """Fold every packed conv weight gradient into its parameter-layout gradient (one launch)."""
+        if self._unpack_n:
+            from . import _C
+            _C.call("saunet_unpack_wgrad_multi", self._unpack_table.data_ptr(), self._unpack_n, self._unpack_total,
+                    self.packed.data_ptr(), self.flat.data_ptr(), stream)
+
     def zero(self):
-        self.flat.zero_()
+        self.flat.zero_()          # (the packed images are cleared by the unpack kernel as it consumes them)
 
     def all_reduce(self, group=None):
         """SUM-reduce in place and scale by 1/world (mean over ranks)."""

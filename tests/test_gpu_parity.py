@@ -307,6 +307,41 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 3, 64, 64))
 
 
+def test_grad_arena_matches_autograd_grads():
+    """Flat GradArena path (packed conv-weight gradient images folded by ONE saunet_unpack_wgrad_multi launch, which
+    also clears them) against the plain path (per-conv temporaries, autograd-returned .grad): same gradients, and a
+    second backward without arena.zero() accumulates exactly once more."""
+    from loss import DualLoss
+    from saunet_b200.parallel import GradArena
+    d = {k: v.to(DEV) for k, v in synth.synthetic_batch(2, 64, seed=304).items()}
+
+    def step(m):
+        bn = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+        seg, edge = m(d["image"])
+        DualLoss()((seg, edge), (d["seg"], d["edge"])).backward()
+        m.load_state_dict(bn, strict=False)
+        torch.cuda.synchronize()
+
+    plain = _model(True)
+    step(plain)
+    ref = {k: p.grad.clone() for k, p in plain.named_parameters() if p.grad is not None}
+    m = _model(True)
+    arena = GradArena(m)
+    step(m)
+    got = dict(m.named_parameters())
+    for k in ("final.weight", "dec0.0.weight", "dec1.block.1.weight", "dec2.c3x3rb.0.weight", "gate1.weight"):
+        assert rel_err(got[k].grad.cpu(), ref[k].cpu()) < 2e-3, k
+    tot = torch.cat([ref[k].flatten() for k, p in m.named_parameters() if k in ref])
+    mine = torch.cat([p.grad.flatten() for k, p in m.named_parameters() if k in ref])
+    assert float((mine - tot).norm() / tot.norm()) < 5e-2
+    assert float(arena.packed.abs().max()) == 0.0          # consumed images are all-zero again
+    first = arena.flat.clone()
+    step(m)                                                 # no arena.zero(): gradients accumulate
+    o = arena.offsets[id(m.final.weight)]
+    n = m.final.weight.numel()
+    assert rel_err(arena.flat[o:o + n].cpu(), 2 * first[o:o + n].cpu()) < 1e-3
+
+
 def test_graphed_step_matches_eager():
     """saunet_b200.graphs.GraphedStep (CUDA-graph replay of fwd+loss+bwd) reproduces the eager step: same loss and
     gradients, picks up in-place weight updates (the pack kernels are inside the graph) and new inputs."""
