@@ -4,6 +4,7 @@
 // per pixel, <= 40x40 MACs): one thread per pixel, weights broadcast from shared memory, no tensor cores, any
 // channel count / alignment.  Same descriptor and the same fused prologue / epilogue as the GEMM kernels.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace saunet {
 
@@ -100,6 +101,126 @@ __global__ void __launch_bounds__(kSkTile) skinny_fwd_kernel(const SkP p) {
     }
 }
 
+
+// ---- forward, row-per-thread variant (16-byte aligned rows) -------------------------------------------------------
+// One thread = one pixel: its input row is read with up to 10 independent 128-bit loads straight into registers (all
+// in flight at once), the [Cin][CO] weights are broadcast from shared memory four at a time (LDS.128 : FFMA = 1 : 4)
+// and the output row is written with 128-bit stores.  No shared-memory staging of activations, no block barriers in
+// the pixel loop.  (The staged kernel above is kept for unaligned rows.)
+template <int CO, int CI4, bool STATS>
+__global__ void __launch_bounds__(kSkTile) skinny_fwd_row_kernel(const SkP p) {
+    __shared__ __align__(16) float Ws[4 * CI4 * CO];
+    __shared__ __align__(16) float bs[CO];
+    __shared__ float scs[4 * CI4], shs[4 * CI4];
+    __shared__ float red[kSkTile / 32][2 * CO];
+    const saunet_conv_desc& d = p.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Cin = d.Cin, Cout = d.Cout;
+    for (int i = tid; i < 4 * CI4 * CO; i += kSkTile) {
+        const int c = i / CO, n = i - c * CO;
+        Ws[i] = (c < Cin && n < Cout) ? d.w[(size_t)c * Cout + n] : 0.f;
+    }
+    for (int i = tid; i < CO; i += kSkTile) bs[i] = (d.bias && i < Cout) ? d.bias[i] : 0.f;
+    for (int i = tid; i < 4 * CI4; i += kSkTile) {
+        scs[i] = (d.in_scale && i < Cin) ? d.in_scale[i] : 1.f; shs[i] = (d.in_scale && i < Cin) ? d.in_shift[i] : 0.f;
+    }
+    __syncthreads();
+    const int ci4 = (Cin + 3) >> 2;
+    const bool vout = (Cout % 4 == 0) && (d.y_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15u) == 0);
+    float ssum[STATS ? CO : 1], ssq[STATS ? CO : 1];
+    if (STATS) {
+#pragma unroll
+        for (int n = 0; n < CO; ++n) { ssum[n] = 0.f; ssq[n] = 0.f; }
+    }
+    for (long long m = (long long)blockIdx.x * kSkTile + tid; m < p.M; m += (long long)gridDim.x * kSkTile) {
+        const float4* xr = reinterpret_cast<const float4*>(d.x + (size_t)m * d.x_ld);
+        float4 xv[CI4];
+#pragma unroll
+        for (int j = 0; j < CI4; ++j) xv[j] = (j < ci4) ? __ldg(xr + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float acc[CO];
+#pragma unroll
+        for (int n = 0; n < CO; ++n) acc[n] = bs[n];
+#pragma unroll
+        for (int j = 0; j < CI4; ++j) {
+            if (j < ci4) {                                   // block-uniform
+                const float xs[4] = {xv[j].x, xv[j].y, xv[j].z, xv[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * j + e;
+                    float x1 = xs[e];
+                    if (c >= Cin) x1 = 0.f;                  // row padding may hold anything
+                    else if (d.in_scale) { x1 = fmaf(x1, scs[c], shs[c]); if (d.in_relu) x1 = fmaxf(x1, 0.f); }
+                    const float4* wr = reinterpret_cast<const float4*>(Ws + c * CO);
+#pragma unroll
+                    for (int q4 = 0; q4 < CO / 4; ++q4) {
+                        const float4 w4 = wr[q4];
+                        acc[4 * q4] = fmaf(x1, w4.x, acc[4 * q4]); acc[4 * q4 + 1] = fmaf(x1, w4.y, acc[4 * q4 + 1]);
+                        acc[4 * q4 + 2] = fmaf(x1, w4.z, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(x1, w4.w, acc[4 * q4 + 3]);
+                    }
+                }
+            }
+        }
+        const float rs = d.row_scale ? (d.row_scale[m] + d.row_scale_add) : 1.f;
+        float* yr = d.y + (size_t)m * d.y_ld;
+        if (STATS) {
+#pragma unroll
+            for (int n = 0; n < CO; ++n) { ssum[n] += acc[n]; ssq[n] = fmaf(acc[n], acc[n], ssq[n]); }
+        }
+#pragma unroll
+        for (int n = 0; n < CO; ++n) acc[n] = apply_act(acc[n] * rs, d.act);
+        if (vout) {
+#pragma unroll
+            for (int q4 = 0; q4 < CO / 4; ++q4) {
+                if (4 * q4 < Cout) {
+                    float4 o = make_float4(acc[4 * q4], acc[4 * q4 + 1], acc[4 * q4 + 2], acc[4 * q4 + 3]);
+                    float4* dst = reinterpret_cast<float4*>(yr) + q4;
+                    if (d.accumulate) { const float4 c4 = *dst; o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w; }
+                    *dst = o;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int n = 0; n < CO; ++n)
+                if (n < Cout) yr[n] = d.accumulate ? yr[n] + acc[n] : acc[n];
+        }
+    }
+    if (STATS) {
+#pragma unroll
+        for (int n = 0; n < CO; ++n) {
+            const float a = warp_sum(ssum[n]), b = warp_sum(ssq[n]);
+            if (lane == 0) { red[warp][n] = a; red[warp][CO + n] = b; }
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * CO; i += kSkTile) {
+            const int n = i % CO;
+            if (n < Cout) {
+                float sacc = 0.f;
+#pragma unroll
+                for (int w = 0; w < kSkTile / 32; ++w) sacc += red[w][i];
+                atomicAdd((i < CO ? d.stat_sum : d.stat_sumsq) + n, (double)sacc);
+            }
+        }
+    }
+}
+
+template <int CO, int CI4>
+static int launch_sk_row(const SkP& p, cudaStream_t st) {
+    long long blocks = ((long long)p.M + kSkTile - 1) / kSkTile;
+    const long long cap = (long long)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    if (p.d.stat_sum) skinny_fwd_row_kernel<CO, CI4, true><<<(int)blocks, kSkTile, 0, st>>>(p);
+    else skinny_fwd_row_kernel<CO, CI4, false><<<(int)blocks, kSkTile, 0, st>>>(p);
+    SAUNET_CHECK_LAUNCH("skinny_fwd_row_kernel");
+    return SAUNET_OK;
+}
+template <int CO>
+static int launch_sk_row_ci(const SkP& p, cudaStream_t st) {
+    const int ci4 = (p.d.Cin + 3) / 4;
+    if (ci4 <= 2) return launch_sk_row<CO, 2>(p, st);
+    if (ci4 <= 5) return launch_sk_row<CO, 5>(p, st);
+    return launch_sk_row<CO, 10>(p, st);
+}
+
 template <int CO>
 static int launch_sk(const SkP& p, cudaStream_t st) {
     long long blocks = ((long long)p.M + kSkTile - 1) / kSkTile;
@@ -123,6 +244,14 @@ int conv_fwd_skinny(const saunet_conv_desc* d, cudaStream_t st) {
     const long long M = (long long)d->B * d->Hg * d->Wg;
     SAUNET_CHECK_ARG(M > 0 && M < (1ll << 31), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd(skinny): bad M=%lld", M);
     p.M = (int)M;
+    if (d->x_ld % 4 == 0 && aligned16(d->x) && !getenv("SAUNET_SKINNY_OLD")) {      // 16-byte aligned rows: row-per-thread kernel
+        if (d->Cout <= 4) return launch_sk_row_ci<4>(p, st);
+        if (d->Cout <= 8) return launch_sk_row_ci<8>(p, st);
+        if (d->Cout <= 16) return launch_sk_row_ci<16>(p, st);
+        if (d->Cout <= 24) return launch_sk_row_ci<24>(p, st);
+        if (d->Cout <= 32) return launch_sk_row_ci<32>(p, st);
+        return launch_sk_row_ci<kSkMaxC>(p, st);
+    }
     if (d->Cout <= 1) return launch_sk<1>(p, st);
     if (d->Cout <= 4) return launch_sk<4>(p, st);
     if (d->Cout <= 8) return launch_sk<8>(p, st);
@@ -200,6 +329,8 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const saunet_wgrad_de
             }
     }
 }
+
+
 
 bool conv_wgrad_skinny_eligible(const saunet_wgrad_desc* d) {
     if (d->KH != 1 || d->KW != 1 || d->sy != 1 || d->sx != 1 || d->offy != 0 || d->offx != 0) return false;
