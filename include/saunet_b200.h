@@ -38,6 +38,8 @@ int saunet_version(void);
 const char* saunet_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 long long saunet_launch_count(void);
+/* kernel family launched by this thread's most recent call (e.g. "conv_wgrad_halo_kernel"): bench.py's roofline attribution */
+const char* saunet_last_kernel(void);
 
 /* ---- implicit-GEMM convolution --------------------------------------------------------------
  * One descriptor drives forward, data-gradient and (with saunet_conv2d_wgrad) weight-gradient of

@@ -11,6 +11,9 @@ void set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+static thread_local const char* g_last_kernel = "";
+void note_kernel(const char* name) { g_last_kernel = name; }
+const char* last_kernel() { return g_last_kernel; }
 int conv_fwd_simt(const saunet_conv_desc* d, cudaStream_t st);
 int conv_wgrad_simt(const saunet_wgrad_desc* d, cudaStream_t st);
 int conv_fwd_tc(const saunet_conv_desc* d, cudaStream_t st);
@@ -34,6 +37,7 @@ using namespace saunet;
 extern "C" int saunet_version(void) { return 100; }
 extern "C" const char* saunet_last_error(void) { return g_err; }
 extern "C" long long saunet_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" const char* saunet_last_kernel(void) { return saunet::last_kernel(); }
 
 extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
     SAUNET_CHECK_ARG(d && d->x && d->w && d->y, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: null pointer");

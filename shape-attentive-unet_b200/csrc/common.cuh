@@ -10,6 +10,7 @@ namespace saunet {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void note_kernel(const char* name);          // name of the kernel family the last C-ABI call launched (saunet_last_kernel)
 
 #define SAUNET_CHECK_ARG(cond, code, ...)                         \
     do {                                                          \
@@ -24,6 +25,7 @@ void count_launch(int n = 1);
             return SAUNET_ERR_CUDA;                                                    \
         }                                                                              \
         saunet::count_launch();                                                        \
+        saunet::note_kernel(name);                                                     \
     } while (0)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

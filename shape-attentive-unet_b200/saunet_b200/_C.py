@@ -77,6 +77,7 @@ _SPECIAL = {
     "saunet_version": ([], c_int),
     "saunet_last_error": ([], c_char_p),
     "saunet_launch_count": ([], c_longlong),
+    "saunet_last_kernel": ([], c_char_p),
     "saunet_canny_workspace_bytes": ([_I, _I, _I], c_longlong),
     "saunet_tc_tile_n": ([_I], c_int),
     "saunet_tc_chunk_major": ([_I, _I], c_int),
@@ -131,7 +132,8 @@ def call(name, *args, flops=0, nbytes=0, tag=""):
         e0.record()
         rc = getattr(load(), name)(*args)
         e1.record()
-        PROFILE.append((name, e0, e1, flops, nbytes, tag))
+        kern = load().saunet_last_kernel()
+        PROFILE.append((name, e0, e1, flops, nbytes, tag, kern.decode() if kern else name))
     else:
         rc = getattr(load(), name)(*args)
     if rc != 0:

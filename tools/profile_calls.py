@@ -22,7 +22,7 @@ _C.PROFILE = []
 step(); torch.cuda.synchronize()
 prof, _C.PROFILE = _C.PROFILE, None
 agg = collections.OrderedDict()
-for name, a, b, fl, nb, tag in prof:
+for name, a, b, fl, nb, tag, _k in prof:
     e = agg.setdefault((name, tag), [0.0, 0, 0.0, 0.0]); e[0] += a.elapsed_time(b); e[1] += 1; e[2] += fl; e[3] += nb
 tot = sum(e[0] for e in agg.values())
 print("total %.2f ms over %d calls" % (tot, len(prof)))
