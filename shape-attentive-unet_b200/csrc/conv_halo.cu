@@ -13,6 +13,7 @@
 // Warps: 0-7 patch producers then epilogue, 8 MMA issuer (+TMEM alloc), 9 weight-tile loader (cp.async.bulk; same
 // chunk-major tiled weight image as conv_tc.cu).  Patch double-buffered; weight tiles in a ring.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace saunet {
 
@@ -324,7 +325,10 @@ bool conv_halo_eligible(const saunet_conv_desc* d) {
     return true;
 }
 
+int conv_fwd_halo_persist(const saunet_conv_desc* d, cudaStream_t st);      // conv_halo_persist.cu
+
 int conv_fwd_halo(const saunet_conv_desc* d, cudaStream_t st) {
+    if (d->tc_bn == 128 && !getenv("SAUNET_HALO_V1")) return conv_fwd_halo_persist(d, st);     // wide tiles: persistent kernel
     HaloP p; p.d = *d;
     p.tiles_x = d->Win / 8; p.tiles_y = d->Hin / 16; p.nchunk = d->Cin / 32; p.wt = d->w_tc;
     const bool three = d->tc_passes != 1;
