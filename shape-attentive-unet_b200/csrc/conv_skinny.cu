@@ -332,6 +332,124 @@ __global__ void __launch_bounds__(256) skinny_wgrad_kernel(const saunet_wgrad_de
 
 
 
+// ---- weight gradient, cp.async-pipelined pixel-split variant -------------------------------------------------------
+// dw[cb][ca] += sum_m pro(Q[m][cb]) * P[m][ca].  The kernel above keeps a padded 40x40 outer product on 100 threads
+// and exposes one global-load latency per 64-pixel chunk, so every call costs >= 0.15 ms whatever the channel counts.
+// Here (a) chunks of 64 pixels stream through a 4-stage cp.async ring (16-byte copies when the rows are 16-byte
+// aligned, 4-byte copies otherwise; rows past the range are zero-filled), (b) the NT = ceil(Cb/4)*ceil(Ca/4) register
+// tiles are spread over all 256 threads: thread (tile t, pixel group g) accumulates pixels g, g+G, ... (G = 256/NT),
+// applying the BN+ReLU prologue to its 4 Q channels on the fly, and (c) the G partial tiles are combined once per
+// block through shared-memory atomics.  Work scales with Cb*Ca.
+constexpr int kSwStages = 4;
+constexpr int kSwPitch = kSkMaxC + 4;                      // 44 floats: rows 16-byte aligned
+
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+    const unsigned n = valid ? 16u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+    const unsigned n = valid ? 4u : 0u;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(n) : "memory");
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(256) skinny_wgrad_async_kernel(const saunet_wgrad_desc d, long long M, long long pix_per_block) {
+    extern __shared__ __align__(16) float sw_smem[];
+    float (*Qs)[kSkPix][kSwPitch] = reinterpret_cast<float (*)[kSkPix][kSwPitch]>(sw_smem);
+    float (*Ps)[kSkPix][kSwPitch] = reinterpret_cast<float (*)[kSkPix][kSwPitch]>(sw_smem + kSwStages * kSkPix * kSwPitch);
+    __shared__ float red[100 * 16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cb4 = (d.Cb + 3) >> 2, ca4 = (d.Ca + 3) >> 2;
+    const int NT = cb4 * ca4, G = 256 / NT;
+    const int t = tid % NT, g = tid / NT;
+    const bool worker = g < G;
+    const int tb = t / ca4, ta = t - tb * ca4;
+    for (int i = tid; i < NT * 16; i += 256) red[i] = 0.f;
+    const long long mbeg = (long long)blockIdx.x * pix_per_block;
+    long long mend = mbeg + pix_per_block; if (mend > M) mend = M;
+    const int nchunk = mend > mbeg ? (int)((mend - mbeg + kSkPix - 1) / kSkPix) : 0;
+    // stage a chunk: warp w copies rows w, w + 8, ...
+    auto issue = [&](int ci) {
+        if (ci < nchunk) {
+            const int st = ci % kSwStages;
+            const long long m0 = mbeg + (long long)ci * kSkPix;
+#pragma unroll
+            for (int k = 0; k < kSkPix / 8; ++k) {
+                const int px = warp + 8 * k;
+                const long long m = m0 + px;
+                const bool rv = m < mend;
+                const float* qrow = d.q + (size_t)(rv ? m : mbeg) * d.q_ld;
+                const float* prow = d.p + (size_t)(rv ? m : mbeg) * d.p_ld;
+                if (ALIGNED) {
+                    if (lane < cb4) cp_async16(&Qs[st][px][lane * 4], qrow + lane * 4, rv);
+                    else if (lane >= 16 && lane - 16 < ca4) cp_async16(&Ps[st][px][(lane - 16) * 4], prow + (lane - 16) * 4, rv);
+                } else {
+                    if (lane < d.Cb) cp_async4(&Qs[st][px][lane], qrow + lane, rv);
+                    if (lane + 32 < d.Cb) cp_async4(&Qs[st][px][lane + 32], qrow + lane + 32, rv);
+                    if (lane < d.Ca) cp_async4(&Ps[st][px][lane], prow + lane, rv);
+                    if (lane + 32 < d.Ca) cp_async4(&Ps[st][px][lane + 32], prow + lane + 32, rv);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // per-thread prologue constants of the tile's 4 Q channels; channels >= Cb contribute zero
+    float qs[4], qh[4]; bool qe[4], pe[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int c = tb * 4 + e;
+        qe[e] = worker && c < d.Cb; pe[e] = ta * 4 + e < d.Ca;
+        qs[e] = (d.q_scale && qe[e]) ? d.q_scale[c] : 1.f; qh[e] = (d.q_scale && qe[e]) ? d.q_shift[c] : 0.f;
+    }
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int s0 = 0; s0 < kSwStages - 1; ++s0) issue(s0);
+    for (int ci = 0; ci < nchunk; ++ci) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kSwStages - 2) : "memory");
+        __syncthreads();                                   // chunk ci landed for everyone; chunk ci-1 fully consumed
+        issue(ci + kSwStages - 1);                         // refills the buffer of chunk ci-1
+        if (worker) {
+            const int st = ci % kSwStages;
+            const long long m0 = mbeg + (long long)ci * kSkPix;
+            int npx = (int)(mend - m0 < kSkPix ? mend - m0 : kSkPix);
+            for (int px = g; px < npx; px += G) {
+                const float4 q4 = *reinterpret_cast<const float4*>(&Qs[st][px][tb * 4]);
+                const float4 p4 = *reinterpret_cast<const float4*>(&Ps[st][px][ta * 4]);
+                float qa[4] = {q4.x, q4.y, q4.z, q4.w};
+                float pa[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float q = qa[e];
+                    if (d.q_scale) { q = fmaf(q, qs[e], qh[e]); if (d.q_relu) q = fmaxf(q, 0.f); }
+                    qa[e] = qe[e] ? q : 0.f;                 // (row padding may hold anything)
+                    pa[e] = pe[e] ? pa[e] : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(qa[i], pa[j], acc[i][j]);
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (worker) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(&red[t * 16 + i * 4 + j], acc[i][j]);
+    }
+    __syncthreads();
+    for (int i = tid; i < NT * 16; i += 256) {
+        const int tt = i >> 4, k = i & 15;
+        const int cb = (tt / ca4) * 4 + (k >> 2), ca = (tt % ca4) * 4 + (k & 3);
+        if (cb < d.Cb && ca < d.Ca) atomicAdd(d.dw + (size_t)cb * d.Ca + ca, red[i]);
+    }
+}
+
 bool conv_wgrad_skinny_eligible(const saunet_wgrad_desc* d) {
     if (d->KH != 1 || d->KW != 1 || d->sy != 1 || d->sx != 1 || d->offy != 0 || d->offx != 0) return false;
     if (d->Hg != d->Hq || d->Wg != d->Wq) return false;
@@ -346,6 +464,23 @@ int conv_wgrad_skinny(const saunet_wgrad_desc* d, cudaStream_t st) {
     long long ppb = (M + blocks - 1) / blocks;
     ppb = (ppb + kSkPix - 1) / kSkPix * kSkPix;
     blocks = (M + ppb - 1) / ppb;
+    if (!getenv("SAUNET_SKINNY_OLD")) {
+        const int smem = 2 * kSwStages * kSkPix * kSwPitch * 4;               // 90 KB: two blocks per SM
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(skinny_wgrad_async_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(skinny_wgrad_async_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_set = true;
+        }
+        long long nb = (long long)kNumSMs * 2;
+        long long pb = (M + nb - 1) / nb; pb = (pb + kSkPix - 1) / kSkPix * kSkPix;
+        nb = (M + pb - 1) / pb;
+        const bool al = d->q_ld % 4 == 0 && d->p_ld % 4 == 0 && aligned16(d->q) && aligned16(d->p);
+        if (al) skinny_wgrad_async_kernel<true><<<(int)nb, 256, smem, st>>>(*d, M, pb);
+        else skinny_wgrad_async_kernel<false><<<(int)nb, 256, smem, st>>>(*d, M, pb);
+        SAUNET_CHECK_LAUNCH("skinny_wgrad_async_kernel");
+        return SAUNET_OK;
+    }
     skinny_wgrad_kernel<<<(int)blocks, 256, 0, st>>>(*d, M, ppb);
     SAUNET_CHECK_LAUNCH("skinny_wgrad_kernel");
     return SAUNET_OK;
