@@ -298,6 +298,44 @@ def test_saunet_vs_oracle_fresh_seed(precision):
         assert rel_err(params[k].grad.cpu(), r["grads"][k]) < 5e-3, k
 
 
+def test_full_size_batch16_properties():
+    """BASELINE configs[1] size (batch 16, 256x256) through size-independent properties, since the oracle is too slow
+    there: (a) eval-mode outputs are per-slice functions -- slice i of the batch-16 forward equals the same slice run
+    alone (different tile / CTA decomposition, same arithmetic class);
+    (b) the training step's loss is finite, every parameter receives a finite gradient, and the gradient is linear in
+    the loss scale (backward of 2*loss == 2 * backward of loss, up to atomic-ordering noise at the top of the net)."""
+    from loss import DualLoss
+    data = synth.synthetic_batch(16, 256, seed=304)
+    x = data["image"].to(DEV)
+    m = _model(False)
+    with torch.no_grad():
+        seg16, edge16 = m(x)
+        for i in (0, 7, 15):
+            seg1, edge1 = m(x[i:i + 1].contiguous())
+            assert rel_err(seg16[i:i + 1].cpu(), seg1.cpu()) < 2e-5, i
+            assert float((edge16[i:i + 1] - edge1).abs().max()) < 1e-5, i
+    del seg16, edge16
+    mt = _model(True)
+    grads = []
+    for scale in (1.0, 2.0):
+        bn = {k: v.clone() for k, v in mt.state_dict().items() if "running" in k or "num_batches" in k}
+        mt.zero_grad(set_to_none=True)
+        seg, edge = mt(x)
+        loss = DualLoss()((seg, edge), (data["seg"], data["edge"]))
+        assert torch.isfinite(loss)
+        (loss * scale).backward()
+        mt.load_state_dict(bn, strict=False)
+        grads.append({k: p.grad.clone() for k, p in mt.named_parameters() if p.grad is not None})
+    assert len(grads[0]) == len(grads[1]) and len(grads[0]) > 500
+    for k, g1 in grads[0].items():
+        assert torch.isfinite(g1).all(), k
+    for k in ("final.weight", "dec0.0.weight", "dec1.block.1.weight"):
+        assert rel_err(grads[1][k].cpu(), 2 * grads[0][k].cpu()) < 2e-3, k
+    a = torch.cat([v.flatten() for v in grads[0].values()])
+    b = torch.cat([v.flatten() for v in grads[1].values()])
+    assert float((b - 2 * a).norm() / (2 * a).norm()) < 5e-2
+
+
 def test_no_cpu_fallback():
     from models import SAUNet
     with warnings.catch_warnings():
