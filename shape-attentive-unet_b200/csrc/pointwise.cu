@@ -106,6 +106,35 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restri
     }
 }
 
+// single-channel maps upsampled by a large factor (the c3/c4/c5 heads, x8 / x16): a thread-per-input-pixel gather walks
+// up to 34x34 candidates serially on only B*Hin*Win threads; here one WARP owns an input pixel and its lanes split the
+// candidate window, then shuffle-reduce (still deterministic, no atomics).
+__global__ void __launch_bounds__(256) bilinear_bwd_c1_warp_kernel(const float* __restrict__ dy, int dy_ld, int B, int Hin, int Win,
+                                                                   float* dx, int dx_ld, int Hout, int Wout, float sh, float sw, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long n = (long long)B * Hin * Win;
+    for (long long p = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; p < n; p += nw) {
+        const int ix = (int)(p % Win); const long long q = p / Win; const int iy = (int)(q % Hin); const int b = (int)(q / Hin);
+        int oylo = 0, oyhi = Hout - 1, oxlo = 0, oxhi = Wout - 1;
+        if (sh > 0.f) { oylo = max(0, (int)floorf((float)(iy - 1) / sh) - 1); oyhi = min(Hout - 1, (int)ceilf((float)(iy + 1) / sh) + 1); }
+        if (sw > 0.f) { oxlo = max(0, (int)floorf((float)(ix - 1) / sw) - 1); oxhi = min(Wout - 1, (int)ceilf((float)(ix + 1) / sw) + 1); }
+        const int ww = oxhi - oxlo + 1, cnt = (oyhi - oylo + 1) * ww;
+        const float* base = dy + (size_t)b * Hout * Wout * dy_ld;
+        float acc = 0.f;
+        for (int k = lane; k < cnt; k += 32) {
+            const int oy = oylo + k / ww, ox = oxlo + k % ww;
+            int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+            src_index(sh, oy, Hin, y0, y1, ly0, ly1);
+            src_index(sw, ox, Win, x0, x1, lx0, lx1);
+            const float w = ((y0 == iy ? ly0 : 0.f) + (y1 == iy ? ly1 : 0.f)) * ((x0 == ix ? lx0 : 0.f) + (x1 == ix ? lx1 : 0.f));
+            if (w != 0.f) acc = fmaf(w, __ldg(base + ((size_t)oy * Wout + ox) * dy_ld), acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) { float* dp = dx + (size_t)p * dx_ld; *dp = accumulate ? *dp + acc : acc; }
+    }
+}
+
 // ---- 2x2 pools ----------------------------------------------------------------------------------------
 template <int VEC, bool MAXP>
 __global__ void __launch_bounds__(256) pool2_fwd_kernel(const float* __restrict__ x, int x_ld, int B, int Hin, int Win, int C,
@@ -304,6 +333,27 @@ __global__ void __launch_bounds__(256) rowscale_bwd_kernel(const float* __restri
     }
 }
 
+// vector variant: LPP = C/4 lanes per pixel (1, 2, 4 or 8), each lane one 128-bit chunk; 32/LPP pixels per warp
+template <int LPP>
+__global__ void __launch_bounds__(256) rowscale_bwd4_kernel(const float* __restrict__ dout, int do_ld, const float* __restrict__ out, int o_ld,
+                                                            const float* __restrict__ alpha, long long npix, float* __restrict__ du,
+                                                            int du_ld, float* dalpha, int da_acc) {
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long nthr = (long long)gridDim.x * blockDim.x;
+    const int sub = (int)(tid % LPP);
+    for (long long p = tid / LPP; p < npix; p += nthr / LPP) {            // (npix tail: whole LPP groups stay together)
+        const float a1 = __ldg(alpha + p) + 1.f;
+        const float inv = 1.f / a1;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(dout + (size_t)p * do_ld) + sub);
+        const float4 o = __ldg(reinterpret_cast<const float4*>(out + (size_t)p * o_ld) + sub);
+        *(reinterpret_cast<float4*>(du + (size_t)p * du_ld) + sub) = make_float4(g.x * a1, g.y * a1, g.z * a1, g.w * a1);
+        float acc = (g.x * o.x + g.y * o.y + g.z * o.z + g.w * o.w) * inv;
+#pragma unroll
+        for (int off = LPP / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (sub == 0) dalpha[p] = da_acc ? dalpha[p] + acc : acc;
+    }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) copy_slice_kernel(const float* __restrict__ src, int s_ld, float* dst, int d_ld, int C, long long npix, int accumulate) {
     const int L = C / VEC;
@@ -372,6 +422,11 @@ extern "C" int saunet_bilinear_bwd(const float* dy, int dy_ld, int B, int Hin, i
     SAUNET_CHECK_ARG(dy && dx && B > 0 && Hin > 0 && Win > 0 && C > 0 && Hout > 0 && Wout > 0, SAUNET_ERR_BAD_SHAPE, "bilinear_bwd: bad args");
     float sh = Hout > 1 ? (float)(Hin - 1) / (float)(Hout - 1) : 0.f, sw = Wout > 1 ? (float)(Win - 1) / (float)(Wout - 1) : 0.f;
     long long n = (long long)B * Hin * Win;
+    if (C == 1 && (long long)Hout * Wout >= 16ll * Hin * Win) {
+        bilinear_bwd_c1_warp_kernel<<<ew_blocks(n * 32), 256, 0, ST>>>(dy, dy_ld, B, Hin, Win, dx, dx_ld, Hout, Wout, sh, sw, accumulate);
+        SAUNET_CHECK_LAUNCH("bilinear_bwd_c1_warp_kernel");
+        return SAUNET_OK;
+    }
     if (vec4(C, dy, dy_ld, dx, dx_ld)) bilinear_bwd_kernel<4><<<ew_blocks(n * (C / 4)), 256, 0, ST>>>(dy, dy_ld, B, Hin, Win, C, dx, dx_ld, Hout, Wout, sh, sw, accumulate);
     else bilinear_bwd_kernel<1><<<ew_blocks(n * C), 256, 0, ST>>>(dy, dy_ld, B, Hin, Win, C, dx, dx_ld, Hout, Wout, sh, sw, accumulate);
     SAUNET_CHECK_LAUNCH("bilinear_bwd_kernel");
@@ -452,6 +507,18 @@ extern "C" int saunet_dualatt_combine_bwd(const float* dout, int do_ld, const fl
 }
 extern "C" int saunet_rowscale_bwd(const float* dout, int do_ld, const float* out, int o_ld, const float* alpha, int C, long long npix, float* du, int du_ld, float* dalpha, int da_acc, void* stream) {
     SAUNET_CHECK_ARG(dout && out && alpha && du && dalpha && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "rowscale_bwd: bad args");
+    const int lpp = C / 4;
+    if (C % 4 == 0 && (lpp == 1 || lpp == 2 || lpp == 4 || lpp == 8) && do_ld % 4 == 0 && o_ld % 4 == 0 && du_ld % 4 == 0 &&
+        aligned16(dout) && aligned16(out) && aligned16(du)) {
+        // grid-stride loop with the thread count a multiple of 32: every pixel's LPP lanes live in one warp and leave the loop together
+        const int blocks = ew_blocks(npix * lpp);
+        if (lpp == 8) rowscale_bwd4_kernel<8><<<blocks, 256, 0, ST>>>(dout, do_ld, out, o_ld, alpha, npix, du, du_ld, dalpha, da_acc);
+        else if (lpp == 4) rowscale_bwd4_kernel<4><<<blocks, 256, 0, ST>>>(dout, do_ld, out, o_ld, alpha, npix, du, du_ld, dalpha, da_acc);
+        else if (lpp == 2) rowscale_bwd4_kernel<2><<<blocks, 256, 0, ST>>>(dout, do_ld, out, o_ld, alpha, npix, du, du_ld, dalpha, da_acc);
+        else rowscale_bwd4_kernel<1><<<blocks, 256, 0, ST>>>(dout, do_ld, out, o_ld, alpha, npix, du, du_ld, dalpha, da_acc);
+        SAUNET_CHECK_LAUNCH("rowscale_bwd4_kernel");
+        return SAUNET_OK;
+    }
     rowscale_bwd_kernel<<<ew_blocks(npix * 32), 256, 0, ST>>>(dout, do_ld, out, o_ld, alpha, C, npix, du, du_ld, dalpha, da_acc);
     SAUNET_CHECK_LAUNCH("rowscale_bwd_kernel");
     return SAUNET_OK;
