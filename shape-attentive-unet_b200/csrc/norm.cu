@@ -379,6 +379,101 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply4_kernel(const float* __re
     }
 }
 
+
+// per-channel sum / sum of squares, 4-channel vector path (same structure as bn_bwd_reduce4_kernel)
+__global__ void __launch_bounds__(256, 2) channel_stats4_kernel(const float* __restrict__ x, int x_ld, int C, long long npix,
+                                                                double* __restrict__ sum, double* __restrict__ sumsq) {
+    __shared__ double sred[8 * 256];
+    const int L = C >> 2;
+    const BnGeom gm(L);
+    const int tid = threadIdx.x, l = tid % gm.lanes, r = tid / gm.lanes;
+    const bool active = r < gm.rows;
+    const long long stride = (long long)gridDim.x * gm.rows;
+    for (int l0 = 0; l0 < L; l0 += gm.lanes) {
+        const int lg = l0 + l;
+        const bool on = active && lg < L;
+        const int c = lg * 4;
+        double a1[4] = {0.0, 0.0, 0.0, 0.0}, a2[4] = {0.0, 0.0, 0.0, 0.0};
+        if (on) {
+            long long p = (long long)blockIdx.x * gm.rows + r;
+            while (p < npix) {
+                float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int it = 0; it < 8 && p < npix; ++it, p += 4 * stride) {
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const long long pp = p + u * stride;
+                        v[u] = pp < npix ? ld4(x + (size_t)pp * x_ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        s1[0] += v[u].x; s1[1] += v[u].y; s1[2] += v[u].z; s1[3] += v[u].w;
+                        s2[0] = fmaf(v[u].x, v[u].x, s2[0]); s2[1] = fmaf(v[u].y, v[u].y, s2[1]);
+                        s2[2] = fmaf(v[u].z, v[u].z, s2[2]); s2[3] = fmaf(v[u].w, v[u].w, s2[3]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { a1[e] += (double)s1[e]; a2[e] += (double)s2[e]; }
+            }
+        }
+        if (gm.rows > 1) {
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { sred[e * 256 + tid] = a1[e]; sred[(4 + e) * 256 + tid] = a2[e]; }
+            __syncthreads();
+            if (r == 0 && lg < L) {
+                for (int rr = 1; rr < gm.rows; ++rr)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { a1[e] += sred[e * 256 + rr * gm.lanes + l]; a2[e] += sred[(4 + e) * 256 + rr * gm.lanes + l]; }
+            }
+        }
+        if (r == 0 && lg < L) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { atomicAdd(sum + c + e, a1[e]); atomicAdd(sumsq + c + e, a2[e]); }
+        }
+    }
+}
+
+// y = act(x*scale + shift (+ residual)), 4-channel vector path: thread = fixed channel group (constants in registers)
+// x strided pixels, 4 pixels per iteration with the loads issued first
+__global__ void __launch_bounds__(256, 2) affine_act4_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, const float* __restrict__ res, int r_ld,
+                                                             float* __restrict__ y, int y_ld, int C, long long npix, int act) {
+    const int L = C >> 2;
+    const BnGeom gm(L);
+    const int tid = threadIdx.x, l = tid % gm.lanes, r = tid / gm.lanes;
+    if (r >= gm.rows) return;
+    const long long stride = (long long)gridDim.x * gm.rows;
+    for (int l0 = 0; l0 < L; l0 += gm.lanes) {
+        const int lg = l0 + l;
+        if (lg >= L) continue;
+        const int c = lg * 4;
+        const float4 sc = scale ? ld4(scale + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 sh = scale ? ld4(shift + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long p = (long long)blockIdx.x * gm.rows + r; p < npix; p += 4 * stride) {
+            float4 v[4], rv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long pp = p + u * stride;
+                if (pp < npix) {
+                    v[u] = ld4(x + (size_t)pp * x_ld + c);
+                    if (res) rv[u] = ld4(res + (size_t)pp * r_ld + c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long pp = p + u * stride;
+                if (pp < npix) {
+                    float4 t = make_float4(fmaf(v[u].x, sc.x, sh.x), fmaf(v[u].y, sc.y, sh.y), fmaf(v[u].z, sc.z, sh.z), fmaf(v[u].w, sc.w, sh.w));
+                    if (res) { t.x += rv[u].x; t.y += rv[u].y; t.z += rv[u].z; t.w += rv[u].w; }
+                    t.x = apply_act(t.x, act); t.y = apply_act(t.y, act); t.z = apply_act(t.z, act); t.w = apply_act(t.w, act);
+                    *reinterpret_cast<float4*>(y + (size_t)pp * y_ld + c) = t;
+                }
+            }
+        }
+    }
+}
+
 static inline int bn_blocks(int C, long long npix) {
     const int L = C / 4, lanes = L < 256 ? L : 256, rows = 256 / lanes;
     long long want = (npix + (long long)rows * 8 - 1) / ((long long)rows * 8);        // >= 8 pixels per thread when possible
@@ -405,6 +500,11 @@ extern "C" int saunet_channel_stats(const float* x, int ld, int C, long long npi
     SAUNET_CHECK_ARG(x && sum && sumsq && C > 0 && npix > 0 && ld >= C, SAUNET_ERR_BAD_SHAPE, "channel_stats: bad args");
     SAUNET_CHECK_ARG(sumsq >= sum + C, SAUNET_ERR_BAD_SHAPE, "channel_stats: sumsq must follow sum by >= C doubles");
     bool vec = vec_ok(C, {{x, ld}});
+    if (vec) {
+        channel_stats4_kernel<<<bn_blocks(C, npix), 256, 0, (cudaStream_t)stream>>>(x, ld, C, npix, sum, sumsq);
+        SAUNET_CHECK_LAUNCH("channel_stats4_kernel");
+        return SAUNET_OK;
+    }
     StatsOp<1> o1{x, ld}; StatsOp<4> o4{x, ld};
     return launch_reduce(o1, o4, vec, C, npix, sum, (long long)(sumsq - sum), (cudaStream_t)stream, "channel_stats_kernel");
 }
@@ -437,6 +537,11 @@ extern "C" int saunet_affine_act(const float* x, int x_ld, const float* scale, c
     SAUNET_CHECK_ARG(x && y && C > 0 && npix > 0 && x_ld >= C && y_ld >= C, SAUNET_ERR_BAD_SHAPE, "affine_act: bad args");
     SAUNET_CHECK_ARG((scale == nullptr) == (shift == nullptr), SAUNET_ERR_BAD_SHAPE, "affine_act: scale/shift mismatch");
     bool vec = vec_ok(C, {{x, x_ld}, {y, y_ld}, {residual, r_ld}});
+    if (vec && (!scale || (aligned16(scale) && aligned16(shift)))) {
+        affine_act4_kernel<<<bn_blocks(C, npix), 256, 0, (cudaStream_t)stream>>>(x, x_ld, scale, shift, residual, r_ld, y, y_ld, C, npix, act);
+        SAUNET_CHECK_LAUNCH("affine_act4_kernel");
+        return SAUNET_OK;
+    }
     if (vec) affine_act_kernel<4><<<ew_blocks(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(x, x_ld, scale, shift, residual, r_ld, y, y_ld, C, npix, act);
     else affine_act_kernel<1><<<ew_blocks(npix * C), 256, 0, (cudaStream_t)stream>>>(x, x_ld, scale, shift, residual, r_ld, y, y_ld, C, npix, act);
     SAUNET_CHECK_LAUNCH("affine_act_kernel");
