@@ -78,3 +78,33 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_grad_arena_packed_table_layout():
+    """saunet_b200.parallel.GradArena (host logic, CPU): every 4-D (conv) parameter gets a packed-gradient image after
+    the parameter-layout gradients, 16-byte aligned, and the device table handed to saunet_unpack_wgrad_multi lists
+    them with exclusive prefix sums of their element counts (include/saunet_b200.h: saunet_unpack_entry)."""
+    import ctypes as C
+    from saunet_b200 import _C
+    from saunet_b200.parallel import GradArena
+    m = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.ConvTranspose2d(8, 6, 4), torch.nn.Conv2d(6, 5, 1))
+    arena = GradArena(m)
+    convs = [p for p in m.parameters() if p.dim() == 4]
+    assert arena._unpack_n == len(convs) == 3
+    assert arena._unpack_total == sum(p.numel() for p in convs)
+    assert arena.flat.numel() == arena.n_grad and arena.flat_all.numel() == arena.n_grad + arena.packed.numel()
+    assert arena.packed.numel() >= arena._unpack_total
+    raw = bytes(arena._unpack_table.numpy().tobytes())
+    assert len(raw) == C.sizeof(_C.UnpackEntry) * 3 == 40 * 3
+    ents = (_C.UnpackEntry * 3).from_buffer_copy(raw)
+    first = 0
+    for e, p in zip(ents, convs):
+        assert (e.first, e.A, e.Bc, e.T) == (first, p.shape[0], p.shape[1], p.shape[2] * p.shape[3])
+        assert e.grad_off == arena.offsets[id(p)] and e.grad_off % 4 == 0 and e.packed_off % 4 == 0
+        assert arena.packed_ptr(p) == arena.packed.data_ptr() + 4 * e.packed_off
+        assert p.grad.data_ptr() == arena.flat.data_ptr() + 4 * e.grad_off
+        first += p.numel()
+    assert arena.packed_ptr(m[1].weight) is None              # BatchNorm weights have no packed image
+    arena.flat_all.fill_(1.0)
+    arena.zero()
+    assert float(arena.flat.abs().sum()) == 0.0 and float(arena.packed.min()) == 1.0     # zero() leaves the (self-clearing) images alone
