@@ -196,6 +196,7 @@ def run_ours(args):
         # the algorithmic bytes of the captured geometry: traffic ~ algorithmic means no wasted re-reads
         NCU = {"conv_wgrad_halo_kernel": ("profiles/r01_final_wgrad_halo.md", 176.2e6, "B16 128x128 128->32 3x3: 171.4 MB read + 4.8 MB written vs 168 MB algorithmic (Q 134 MB + dY 34 MB)"),
                "conv_halo_kernel": ("profiles/r01_final_halo_n32.md", 153.8e6, "B16 128x128 128->32 3x3: 134.6 MB read + 19.2 MB written vs 168 MB algorithmic"),
+               "conv_halo_persist_kernel": ("profiles/r01_final_halo_persist.md", 73.9e6, "B16 64x64 256->128 3x3: 69.6 MB read + 4.3 MB written (output still in L2) vs 101 MB algorithmic; 68.8 % tensor-pipe active"),
                "conv_tc_kernel": ("profiles/r01_final_tc_1x1.md", 138.1e6, "B16 64x64 480->128 1x1: 126.4 MB read + 11.8 MB written (output still in L2) vs 159 MB algorithmic"),
                "conv_wgrad_pw_kernel": ("profiles/r01_final_wgrad_pw.md", 163.5e6, "B16 64x64 480->128 1x1: 159.8 MB read + 3.7 MB written vs 159 MB algorithmic"),
                "bn_bwd_apply4_kernel": ("profiles/r01_final_bn.md", 364.0e6, "C128 npix262144: 268.5 MB read + 95.6 MB written vs 403 MB algorithmic (dx partly still in L2)"),
