@@ -241,8 +241,13 @@ def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None):
     bn = lib.saunet_tc_tile_n(N)
     if M is not None:
         mt = (M + 127) // 128
-        while bn > 32 and mt * ((N + bn - 1) // bn) < 148:
+        # persistent kernels: a 128-wide tile runs at ~2x the efficiency of the narrow ones (MMA operand traffic vs
+        # math balance at N = 128), so keep it as long as most SMs get a tile; only really small problems trade tile
+        # width for CTA count
+        floor = 96 if bn >= 128 and os.environ.get("SAUNET_WIDE_TILES", "1") == "1" else 148
+        while bn > 32 and mt * ((N + bn - 1) // bn) < floor:
             bn //= 2
+            floor = 148
     key = (id(w), mode, phase, bn, passes)
     ent = _PACK.get(key)
     K = taps * Cin
