@@ -30,6 +30,8 @@ int conv_wgrad_halo(const saunet_wgrad_desc* d, cudaStream_t st);
 bool conv_wgrad_halo_eligible(const saunet_wgrad_desc* d);
 int conv_wgrad_pw(const saunet_wgrad_desc* d, cudaStream_t st);
 bool conv_wgrad_pw_eligible(const saunet_wgrad_desc* d);
+int conv_fwd_pw_t(const saunet_conv_desc* d, cudaStream_t st);
+bool conv_pw_t_eligible(const saunet_conv_desc* d);
 }  // namespace saunet
 
 using namespace saunet;
@@ -52,6 +54,7 @@ extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
     SAUNET_CHECK_ARG(d->act >= 0 && d->act <= 2, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: bad activation %d", d->act);
     if (conv_skinny_eligible(d)) return conv_fwd_skinny(d, (cudaStream_t)stream);
     if (conv_halo_eligible(d) && !getenv("SAUNET_NO_HALO")) return conv_fwd_halo(d, (cudaStream_t)stream);
+    if (conv_pw_t_eligible(d)) return conv_fwd_pw_t(d, (cudaStream_t)stream);      // large 1x1 layers: channels on the TMEM lanes
     if (conv_tc_eligible(d)) return conv_fwd_tc(d, (cudaStream_t)stream);
     return conv_fwd_simt(d, (cudaStream_t)stream);
 }

@@ -33,6 +33,12 @@ CASES = [
     (1, 16, 8, 32, 16, 3, 1, 1, 32, 16, True, False, True, False, ACT_NONE, 0),
     (3, 16, 40, 96, 128, 3, 1, 1, 0, 0, True, True, False, False, ACT_NONE, 1),
     (2, 48, 16, 160, 48, 3, 1, 1, 0, 0, False, False, True, False, ACT_SIGMOID, 0),
+    # large pointwise layers (>= 74 tiles of 256 pixels x 128 channels): also the shapes of the channels-on-lanes kernel
+    # (conv_pw_t.cu)
+    (2, 128, 128, 96, 128, 1, 1, 0, 32, 0, True, False, True, False, ACT_NONE, 0),   # dense conv1: prologue + statistics
+    (1, 150, 150, 64, 160, 1, 1, 0, 0, 0, False, True, True, False, ACT_RELU, 0),    # ragged M, two channel tiles (one partial), bias
+    (1, 160, 160, 128, 256, 1, 1, 0, 0, 64, False, False, False, False, ACT_NONE, 1),  # dgrad-like: accumulate into a slice
+    (1, 192, 192, 40, 128, 1, 1, 0, 0, 0, True, True, False, True, ACT_SIGMOID, 0),  # K padded to 64, row gate, sigmoid
 ]
 
 
