@@ -108,3 +108,21 @@ def test_grad_arena_packed_table_layout():
     arena.flat_all.fill_(1.0)
     arena.zero()
     assert float(arena.flat.abs().sum()) == 0.0 and float(arena.packed.min()) == 1.0     # zero() leaves the (self-clearing) images alone
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference algorithm on the host CPU, the one place outside tests/ and smoke()
+    that executes oracle/): one JSON line with the keys the driver reads, no GPU needed."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["unit"] == "slices/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "config" in d and "workload" in d["config"] and d["dtype"] == "f32"
