@@ -181,9 +181,15 @@ int saunet_nhwc_to_nchw(const float* src, int src_ld, float* dst, int B, int C, 
  * acc = double[2 + 2*C + 1]: [0]=sum w*nll, [1]=sum w, [2..2+C)=I_c, [2+C..2+2C)=Card_c, [2+2C]=sum bce (caller zeroes)
  * parts: bit0 = dice, bit1 = weighted CE, bit2 = edge BCE -- the terms summed into loss[0] and differentiated
  * (DualLoss = 7; loss.dice_loss alone = 1).
- * finalize writes loss[0]=total of the selected parts, [1]=dice, [2]=ce, [3]=bce (float). */
+ * finalize writes loss[0]=total of the selected parts, [1]=dice, [2]=ce, [3]=bce (float).
+ * Labels outside [0,C) are skipped by every sum (never used as an index) and counted in counts[2+3*7].
+ * counts (optional, int[2 + 3*7 + 1], caller zeroes): the training-branch metrics of SegmentationModule
+ * (models/models.py:51-74,92) taken from the same pass: pred = argmax(round(softmax(logits))); [0] = |label>=1 & pred==label|,
+ * [1] = |label>=1|, class i>=1: [2+3(i-1)] = |label==i & pred==i|, [+1] = |label==i|, [+2] = |pred==i|; finalize then also
+ * writes loss[4] = pixel accuracy and loss[4+i] = Jaccard of class i (loss must then hold 4 + C floats). */
 int saunet_dual_loss_fwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
-                         long long npix, int C, const float* class_w, int parts, double* acc, float* loss, void* stream);
+                         long long npix, int C, const float* class_w, int parts, double* acc, float* loss, int* counts,
+                         void* stream);
 int saunet_dual_loss_bwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
                          long long npix, int C, const float* class_w, const double* acc, const float* dloss,
                          float* dlogits, int dl_ld, float* dedge, int parts, void* stream);

@@ -13,7 +13,7 @@
  *   4. hysteresis: mag > high is an edge seed, mag > low candidates survive
  *      iff 8-connected to a seed;  output 255 / 0.
  * Pinned bit-exactly against cv2.Canny by tests/golden/make_golden.py
- * (fixtures tests/golden/canny_*.npz) and tests/test_oracle_canny.py.
+ * (fixtures tests/golden/canny_ref.npz) and tests/test_oracle_vs_golden.py.
  */
 #include <stdint.h>
 #include <stdlib.h>

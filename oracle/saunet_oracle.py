@@ -252,7 +252,7 @@ def prepare_params(state_dict, dtype=torch.float32, requires_grad=False):
     return sd
 
 
-def train_step(state_dict, image, seg_t, edge_t, canny=None, dtype=torch.float32, training=True):
+def train_step(state_dict, image, seg_t, edge_t, canny=None, dtype=torch.float32, training=True, return_att=False):
     """fwd + DualLoss + bwd (train.py:95-104).  Returns dict with logits, edge,
     loss parts, grads (by state_dict key, canonical ``encoder.features.*`` names
     only) and BN running-stat updates."""
@@ -261,9 +261,33 @@ def train_step(state_dict, image, seg_t, edge_t, canny=None, dtype=torch.float32
     # the canonical name only so each parameter has one leaf.
     rec = BNRecorder()
     x = image.to(dtype)
-    seg, edge = saunet_forward(sd, x, training=training, canny=canny, rec=rec)
+    maps = None
+    if return_att:
+        seg, edge, maps = saunet_forward(sd, x, training=training, canny=canny, return_att=True, rec=rec)
+    else:
+        seg, edge = saunet_forward(sd, x, training=training, canny=canny, rec=rec)
     total, dice, ce, bce = dual_loss(seg, edge, seg_t, edge_t, parts=True)
     total.backward()
     grads = {k: v.grad for k, v in sd.items() if v.is_floating_point() and v.requires_grad and v.grad is not None}
-    return {"logits": seg.detach(), "edge": edge.detach(), "loss": total.detach(), "dice": dice.detach(),
-            "ce": ce.detach(), "bce": bce.detach(), "grads": grads, "bn_updates": rec.updates}
+    out = {"logits": seg.detach(), "edge": edge.detach(), "loss": total.detach(), "dice": dice.detach(),
+           "ce": ce.detach(), "bce": bce.detach(), "grads": grads, "bn_updates": rec.updates}
+    if maps is not None:
+        out["maps"] = [t.detach() for t in maps]
+    return out
+
+
+def pixel_metrics(logits, label, num_class):
+    """SegmentationModule's training-branch metrics, models/models.py:51-74 applied as in :92 to
+    round(softmax(logits)): (pixel accuracy over label >= 1, [Jaccard of class 1 .. num_class-1])."""
+    pred = torch.round(F.softmax(logits, dim=1)).long()
+    _, preds = torch.max(pred, dim=1)
+    valid = (label >= 1).long()
+    acc = torch.sum(valid * (preds == label).long()).float() / (torch.sum(valid).float() + 1e-10)
+    jac = []
+    for i in range(1, num_class):
+        v = (label == i).long()
+        p = (preds == i).long()
+        anb = torch.sum(v * p)
+        j = anb.float() / (torch.sum(v).float() + torch.sum(p).float() - anb.float() + 1e-10)
+        jac.append(j if j <= 1 else torch.zeros(()))
+    return acc, jac

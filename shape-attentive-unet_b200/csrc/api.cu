@@ -53,7 +53,7 @@ extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
     SAUNET_CHECK_ARG((d->stat_sum == nullptr) == (d->stat_sumsq == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: stat_sum/stat_sumsq mismatch");
     SAUNET_CHECK_ARG(d->act >= 0 && d->act <= 2, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: bad activation %d", d->act);
     if (conv_skinny_eligible(d)) return conv_fwd_skinny(d, (cudaStream_t)stream);
-    if (conv_halo_eligible(d) && !getenv("SAUNET_NO_HALO")) return conv_fwd_halo(d, (cudaStream_t)stream);
+    if (conv_halo_eligible(d) && !SAUNET_ENV_FLAG("SAUNET_NO_HALO")) return conv_fwd_halo(d, (cudaStream_t)stream);
     if (conv_pw_t_eligible(d)) return conv_fwd_pw_t(d, (cudaStream_t)stream);      // large 1x1 layers: channels on the TMEM lanes
     if (conv_tc_eligible(d)) return conv_fwd_tc(d, (cudaStream_t)stream);
     return conv_fwd_simt(d, (cudaStream_t)stream);
@@ -65,9 +65,9 @@ extern "C" int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream) {
                      d->Wg > 0 && d->sy > 0 && d->sx > 0, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: non-positive dimension");
     SAUNET_CHECK_ARG(d->p_ld >= d->Ca && d->q_ld >= d->Cb, SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: ld smaller than channel count");
     SAUNET_CHECK_ARG((d->q_scale == nullptr) == (d->q_shift == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_wgrad: q_scale/q_shift mismatch");
-    if (conv_wgrad_pw_eligible(d) && !getenv("SAUNET_NO_WGRAD_PW")) return conv_wgrad_pw(d, (cudaStream_t)stream);
+    if (conv_wgrad_pw_eligible(d) && !SAUNET_ENV_FLAG("SAUNET_NO_WGRAD_PW")) return conv_wgrad_pw(d, (cudaStream_t)stream);
     if (conv_wgrad_skinny_eligible(d)) return conv_wgrad_skinny(d, (cudaStream_t)stream);
-    if (conv_wgrad_halo_eligible(d) && !getenv("SAUNET_NO_WGRAD_HALO")) return conv_wgrad_halo(d, (cudaStream_t)stream);
+    if (conv_wgrad_halo_eligible(d) && !SAUNET_ENV_FLAG("SAUNET_NO_WGRAD_HALO")) return conv_wgrad_halo(d, (cudaStream_t)stream);
     if (conv_wgrad_tc_eligible(d)) return conv_wgrad_tc(d, (cudaStream_t)stream);
     return conv_wgrad_simt(d, (cudaStream_t)stream);
 }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "../../include/saunet_b200.h"
 
 namespace saunet {
@@ -31,6 +32,8 @@ void note_kernel(const char* name);          // name of the kernel family the la
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static constexpr int kNumSMs = 148;
+// debugging switches (environment variables) are read ONCE per process, never on the launch path
+#define SAUNET_ENV_FLAG(var) ([]() -> bool { static const bool v = getenv(var) != nullptr; return v; }())
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -168,10 +168,10 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
                     tv.x = fmaf(tv.x, sc.x, sh.x); tv.y = fmaf(tv.y, sc.y, sh.y); tv.z = fmaf(tv.z, sc.z, sh.z); tv.w = fmaf(tv.w, sc.w, sh.w);
                     if (d.in_relu) { tv.x = fmaxf(tv.x, 0.f); tv.y = fmaxf(tv.y, 0.f); tv.z = fmaxf(tv.z, 0.f); tv.w = fmaxf(tv.w, 0.f); }
                 }
-                float4 hi = make_float4(tf32_hi(tv.x), tf32_hi(tv.y), tf32_hi(tv.z), tf32_hi(tv.w));
+                float4 hi = split_hi4(tv);
                 *reinterpret_cast<float4*>(hi_img + s_off[i]) = hi;
                 if (NPASS == 3) {
-                    float4 lo = make_float4(tf32_hi(tv.x - hi.x), tf32_hi(tv.y - hi.y), tf32_hi(tv.z - hi.z), tf32_hi(tv.w - hi.w));
+                    float4 lo = split_lo4(tv, hi);
                     *reinterpret_cast<float4*>(lo_img + s_off[i]) = lo;
                 }
             }

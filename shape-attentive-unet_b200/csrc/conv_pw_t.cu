@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
                     t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
                     if (d.in_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
                 }
-                const float4 hi = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
+                const float4 hi = split_hi4(t);
                 *reinterpret_cast<float4*>(x_hi + s_off[i]) = hi;
                 if (NPASS == 3) {
-                    const float4 lo = make_float4(tf32_hi(t.x - hi.x), tf32_hi(t.y - hi.y), tf32_hi(t.z - hi.z), tf32_hi(t.w - hi.w));
+                    const float4 lo = split_lo4(t, hi);
                     *reinterpret_cast<float4*>(x_lo + s_off[i]) = lo;
                 }
             }

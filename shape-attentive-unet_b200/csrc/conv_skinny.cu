@@ -244,7 +244,7 @@ int conv_fwd_skinny(const saunet_conv_desc* d, cudaStream_t st) {
     const long long M = (long long)d->B * d->Hg * d->Wg;
     SAUNET_CHECK_ARG(M > 0 && M < (1ll << 31), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd(skinny): bad M=%lld", M);
     p.M = (int)M;
-    if (d->x_ld % 4 == 0 && aligned16(d->x) && !getenv("SAUNET_SKINNY_OLD")) {      // 16-byte aligned rows: row-per-thread kernel
+    if (d->x_ld % 4 == 0 && aligned16(d->x) && !SAUNET_ENV_FLAG("SAUNET_SKINNY_OLD")) {      // 16-byte aligned rows: row-per-thread kernel
         if (d->Cout <= 4) return launch_sk_row_ci<4>(p, st);
         if (d->Cout <= 8) return launch_sk_row_ci<8>(p, st);
         if (d->Cout <= 16) return launch_sk_row_ci<16>(p, st);
@@ -464,7 +464,7 @@ int conv_wgrad_skinny(const saunet_wgrad_desc* d, cudaStream_t st) {
     long long ppb = (M + blocks - 1) / blocks;
     ppb = (ppb + kSkPix - 1) / kSkPix * kSkPix;
     blocks = (M + ppb - 1) / ppb;
-    if (!getenv("SAUNET_SKINNY_OLD")) {
+    if (!SAUNET_ENV_FLAG("SAUNET_SKINNY_OLD")) {
         const int smem = 2 * kSwStages * kSkPix * kSwPitch * 4;               // 90 KB: two blocks per SM
         static bool attr_set = false;
         if (!attr_set) {

@@ -196,10 +196,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
                     if (d.in_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
                 }
-                float4 hi = make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w));
+                float4 hi = split_hi4(t);
                 *reinterpret_cast<float4*>(a_hi + s_off[i]) = hi;
                 if (NPASS == 3) {
-                    float4 lo = make_float4(tf32_hi(t.x - hi.x), tf32_hi(t.y - hi.y), tf32_hi(t.z - hi.z), tf32_hi(t.w - hi.w));
+                    float4 lo = split_lo4(t, hi);
                     *reinterpret_cast<float4*>(a_lo + s_off[i]) = lo;
                 }
             }
@@ -460,8 +460,12 @@ static int launch_tc_mode(const TcP& p, cudaStream_t st) {
     TcP q = p;
     q.ntile_n = cdiv(p.d.Cout, BN);
     q.ntiles = cdiv(p.M, 128) * q.ntile_n;
-    const char* pe = getenv("SAUNET_TC_PROF");          // debugging aid: device pointer to long long[148][16]
-    q.prof = pe ? reinterpret_cast<long long*>(strtoull(pe, nullptr, 0)) : nullptr;
+    // debugging aid: device pointer to long long[148][16] (read once per process)
+    static long long* const prof_ptr = []() -> long long* {
+        const char* pe = getenv("SAUNET_TC_PROF");
+        return pe ? reinterpret_cast<long long*>(strtoull(pe, nullptr, 0)) : nullptr;
+    }();
+    q.prof = prof_ptr;
     const int grid = q.ntiles < kNumSMs ? q.ntiles : kNumSMs;
     conv_tc_kernel<BN, NPASS, MODE><<<grid, kTcThreads, Cfg::SMEM, st>>>(q);
     SAUNET_CHECK_LAUNCH("conv_tc_kernel");

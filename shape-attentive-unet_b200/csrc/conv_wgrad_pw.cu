@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(kPwThreads, 1) conv_wgrad_pw_kernel(const __gr
             mask = mk;
         };
         auto split_store = [&](uint8_t* hi_img, uint8_t* lo_img, uint32_t off, const float4& v) {
-            float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-            float4 lo = make_float4(tf32_hi(v.x - hi.x), tf32_hi(v.y - hi.y), tf32_hi(v.z - hi.z), tf32_hi(v.w - hi.w));
+            float4 hi = split_hi4(v);
+            float4 lo = split_lo4(v, hi);
             *reinterpret_cast<float4*>(hi_img + off) = hi;
             *reinterpret_cast<float4*>(lo_img + off) = lo;
         };

@@ -169,8 +169,8 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
                     v.x = fmaf(v.x, qsc.x, qsh.x); v.y = fmaf(v.y, qsc.y, qsh.y); v.z = fmaf(v.z, qsc.z, qsh.z); v.w = fmaf(v.w, qsc.w, qsh.w);
                     if (d.q_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 }
-                float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-                float4 lo = make_float4(tf32_hi(v.x - hi.x), tf32_hi(v.y - hi.y), tf32_hi(v.z - hi.z), tf32_hi(v.w - hi.w));
+                float4 hi = split_hi4(v);
+                float4 lo = split_lo4(v, hi);
                 *reinterpret_cast<float4*>(hi_img + off) = hi;
                 *reinterpret_cast<float4*>(lo_img + off) = lo;
             };

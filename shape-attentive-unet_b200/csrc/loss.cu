@@ -2,6 +2,9 @@
 // Restates loss.py:51-88,149-159 of the reference as two single-pass HBM-bound kernels over the
 // [npix][C] logits: fwd accumulates the 2+2C+1 batch sums (fp64 atomics, one per CTA), bwd recomputes
 // the softmax and emits d(logits) and d(edge) in one pass.
+// The forward pass also counts the training-branch metrics of SegmentationModule (models/models.py:51-74,92:
+// pixel accuracy + per-class Jaccard of round(softmax(logits))) from the softmax it already holds, so the metric
+// costs no extra pass over the logits and no torch kernels.
 #include "common.cuh"
 
 namespace saunet {
@@ -35,21 +38,45 @@ __device__ __forceinline__ void softmax_c(const float* z, int C, float* prob, fl
 
 __global__ void __launch_bounds__(256) dual_loss_fwd_kernel(const float* __restrict__ logits, int l_ld, const float* __restrict__ edge,
                                                             const long long* __restrict__ seg_t, const float* __restrict__ edge_t,
-                                                            long long npix, int C, const float* __restrict__ cw, double* acc) {
+                                                            long long npix, int C, const float* __restrict__ cw, double* acc,
+                                                            int* __restrict__ counts) {
     float q[2 + 2 * kMaxC + 1];
 #pragma unroll
     for (int i = 0; i < 2 + 2 * kMaxC + 1; ++i) q[i] = 0.f;
+    // metric counters: [0] correct & labelled, [1] labelled (label >= 1), then per class i>=1: [2+3(i-1)] = |label==i & pred==i|,
+    // [+1] = |label==i|, [+2] = |pred==i|; last: labels outside [0,C) (skipped by every sum)
+    int cnt[2 + 3 * (kMaxC - 1) + 1];
+#pragma unroll
+    for (int i = 0; i < 2 + 3 * (kMaxC - 1) + 1; ++i) cnt[i] = 0;
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
         float z[kMaxC], pr[kMaxC], lp[kMaxC];
         for (int c = 0; c < C; ++c) z[c] = __ldg(logits + (size_t)p * l_ld + c);
         softmax_c(z, C, pr, lp);
-        const int t = (int)seg_t[p];
-        const float w = cw ? cw[t] : 1.f;
+        const long long tl = seg_t[p];
+        const bool tval = tl >= 0 && tl < C;         // an out-of-range label (255, -100 ...) never indexes anything
+        const int t = tval ? (int)tl : -1;
+        const float w = tval ? (cw ? cw[t] : 1.f) : 0.f;
         for (int c = 0; c < C; ++c) {
             const float oh = (c == t) ? 1.f : 0.f;
             if (c == t) { q[0] -= w * lp[c]; q[1] += w; }
             q[2 + c] += pr[c] * oh;
             q[2 + kMaxC + c] += pr[c] + oh;
+        }
+        if (counts) {
+            // torch.max(round(softmax(z)).long(), dim=1): the first class whose probability rounds to 1 (p > 0.5; exactly
+            // 0.5 rounds to even = 0), class 0 when none does
+            int pred = 0;
+            for (int c = C - 1; c >= 1; --c) if (rintf(pr[c]) == 1.f) pred = c;
+            if (rintf(pr[0]) == 1.f) pred = 0;
+            if (!tval) cnt[2 + 3 * (kMaxC - 1)]++;
+            if (t >= 1) { cnt[1]++; if (pred == t) cnt[0]++; }
+#pragma unroll
+            for (int i = 1; i < kMaxC; ++i) {
+                if (i < C) {
+                    const bool v = t == i, pp = pred == i;
+                    cnt[2 + 3 * (i - 1)] += (v && pp); cnt[3 + 3 * (i - 1)] += v; cnt[4 + 3 * (i - 1)] += pp;
+                }
+            }
         }
         if (edge) {
             const float pe = __ldg(edge + p), te = __ldg(edge_t + p);
@@ -64,10 +91,34 @@ __global__ void __launch_bounds__(256) dual_loss_fwd_kernel(const float* __restr
     for (int c = 0; c < C; ++c) { v[2 + c] = q[2 + c]; v[2 + C + c] = q[2 + kMaxC + c]; }
     v[2 + 2 * C] = q[2 + 2 * kMaxC];
     block_reduce_atomic<2 + 2 * kMaxC + 1>(v, acc, 2 + 2 * C + 1);
+    if (counts) {
+        __shared__ int cred[2 + 3 * (kMaxC - 1) + 1];
+        if (threadIdx.x < 2 + 3 * (kMaxC - 1) + 1) cred[threadIdx.x] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2 + 3 * (kMaxC - 1) + 1; ++i) {
+            int s = cnt[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0 && s) atomicAdd(&cred[i], s);
+        }
+        __syncthreads();
+        if (threadIdx.x < 2 + 3 * (kMaxC - 1) + 1 && cred[threadIdx.x]) atomicAdd(counts + threadIdx.x, cred[threadIdx.x]);
+    }
 }
 
-__global__ void dual_loss_finalize_kernel(const double* __restrict__ acc, long long npix, int C, int has_edge, int parts, float* loss) {
+__global__ void dual_loss_finalize_kernel(const double* __restrict__ acc, long long npix, int C, int has_edge, int parts, float* loss,
+                                          const int* __restrict__ counts) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (counts) {
+        // models/models.py:57-72: acc = correct / (labelled + 1e-10); jaccard_i = anb / (|v| + |p| - anb + 1e-10), 0 if > 1
+        loss[4] = (float)counts[0] / ((float)counts[1] + 1e-10f);
+        for (int i = 1; i < C; ++i) {
+            const float anb = (float)counts[2 + 3 * (i - 1)];
+            const float j = anb / ((float)counts[3 + 3 * (i - 1)] + (float)counts[4 + 3 * (i - 1)] - anb + 1e-10f);
+            loss[4 + i] = j <= 1.f ? j : 0.f;
+        }
+    }
     double ce = acc[0] / acc[1];
     double d = 0.0;
     for (int c = 0; c < C; ++c) d += 2.0 * acc[2 + c] / (acc[2 + C + c] + (double)kDiceEps);
@@ -99,8 +150,9 @@ __global__ void __launch_bounds__(256) dual_loss_bwd_kernel(const float* __restr
         float z[kMaxC], pr[kMaxC], lp[kMaxC], a[kMaxC];
         for (int c = 0; c < C; ++c) z[c] = __ldg(logits + (size_t)p * l_ld + c);
         softmax_c(z, C, pr, lp);
-        const int t = (int)seg_t[p];
-        const float w = (cw ? cw[t] : 1.f) * inv_w;
+        const long long tl = seg_t[p];
+        const int t = (tl >= 0 && tl < C) ? (int)tl : -1;
+        const float w = t >= 0 ? (cw ? cw[t] : 1.f) * inv_w : 0.f;
         float dot = 0.f;
         for (int c = 0; c < C; ++c) { a[c] = (c == t ? k1[c] : 0.f) + k2[c]; dot = fmaf(a[c], pr[c], dot); }
         for (int c = 0; c < C; ++c) {
@@ -119,14 +171,15 @@ __global__ void __launch_bounds__(256) dual_loss_bwd_kernel(const float* __restr
 using namespace saunet;
 
 extern "C" int saunet_dual_loss_fwd(const float* logits, int l_ld, const float* edge, const long long* seg_t, const float* edge_t,
-                                    long long npix, int C, const float* class_w, int parts, double* acc, float* loss, void* stream) {
+                                    long long npix, int C, const float* class_w, int parts, double* acc, float* loss,
+                                    int* counts, void* stream) {
     SAUNET_CHECK_ARG(logits && seg_t && acc && loss && npix > 0, SAUNET_ERR_BAD_SHAPE, "dual_loss_fwd: bad args");
     SAUNET_CHECK_ARG(C >= 2 && C <= kMaxC && l_ld >= C, SAUNET_ERR_BAD_SHAPE, "dual_loss_fwd: C=%d unsupported (2..8)", C);
     SAUNET_CHECK_ARG((edge == nullptr) == (edge_t == nullptr), SAUNET_ERR_BAD_SHAPE, "dual_loss_fwd: edge/edge_t mismatch");
     long long blocks = (npix + 255) / 256; if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-    dual_loss_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, l_ld, edge, seg_t, edge_t, npix, C, class_w, acc);
+    dual_loss_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(logits, l_ld, edge, seg_t, edge_t, npix, C, class_w, acc, counts);
     SAUNET_CHECK_LAUNCH("dual_loss_fwd_kernel");
-    dual_loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, npix, C, edge != nullptr, parts, loss);
+    dual_loss_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(acc, npix, C, edge != nullptr, parts, loss, counts);
     SAUNET_CHECK_LAUNCH("dual_loss_finalize_kernel");
     return SAUNET_OK;
 }

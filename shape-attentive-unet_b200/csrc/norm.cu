@@ -552,7 +552,7 @@ extern "C" int saunet_bn_bwd_reduce(const float* dy, int dy_ld, const float* x, 
                                     const float* state, int C, long long npix, int act, double* red, void* stream) {
     SAUNET_CHECK_ARG(dy && x && state && red && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "bn_bwd_reduce: bad args");
     bool vec = vec_ok(C, {{dy, dy_ld}, {x, x_ld}, {out, out_ld}}) && aligned16(state);
-    if (vec && !getenv("SAUNET_NO_BN4")) {
+    if (vec && !SAUNET_ENV_FLAG("SAUNET_NO_BN4")) {
         const int blocks = bn_blocks(C, npix);
         cudaStream_t st = (cudaStream_t)stream;
         if (act != SAUNET_ACT_RELU) bn_bwd_reduce4_kernel<false, false><<<blocks, 256, 0, st>>>(dy, dy_ld, x, x_ld, out, out_ld, state, C, npix, red);
@@ -573,7 +573,7 @@ extern "C" int saunet_bn_bwd_apply(const float* dy, int dy_ld, const float* x, i
     SAUNET_CHECK_ARG(dy && x && state && red && C > 0 && npix > 0, SAUNET_ERR_BAD_SHAPE, "bn_bwd_apply: bad args");
     SAUNET_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), SAUNET_ERR_BAD_SHAPE, "bn_bwd_apply: dgamma/dbeta mismatch");
     bool vec = vec_ok(C, {{dy, dy_ld}, {x, x_ld}, {out, out_ld}, {dx, dx_ld}, {dres, dres_ld}});
-    if (vec && aligned16(state) && !getenv("SAUNET_NO_BN4")) {
+    if (vec && aligned16(state) && !SAUNET_ENV_FLAG("SAUNET_NO_BN4")) {
         const int blocks = bn_blocks(C, npix);
         cudaStream_t st = (cudaStream_t)stream;
 #define SAUNET_BN_APPLY(R, O) bn_bwd_apply4_kernel<R, O><<<blocks, 256, 0, st>>>(dy, dy_ld, x, x_ld, out, out_ld, state, gamma, red, C, npix, training, dx, dx_ld, dx_acc, dres, dres_ld, dres_acc, dgamma, dbeta)

@@ -70,6 +70,26 @@ __device__ __forceinline__ float tf32_hi(float v) {
 }
 
 
+// Operand split of the activations (3xTF32): x = hi + lo with hi, lo both tf32.
+// kind::tf32 reads only the top 19 bits of each 32-bit operand element (sign, 8 exponent, 10 mantissa bits): it
+// TRUNCATES.  So the "hi" image can hold the fp32 value itself (hi := trunc(x), taken by the hardware for free) and
+// lo := x - trunc(x) is exact in fp32 (<= 13 significant bits, again truncated to 11 by the hardware): 2 ALU ops per
+// element instead of the 5 of a round-to-nearest split, and nothing to store for `hi` when the operand needs no
+// prologue.  Errors: |x - hi - lo_used| <= 2^-21 |x| (one-sided), the dropped lo*lo term <= 2^-20 of the product.
+// -DSAUNET_SPLIT_RN restores the round-to-nearest split (hi = rn(x), lo = rn(x - hi)).
+#ifndef SAUNET_SPLIT_RN
+__device__ __forceinline__ float split_lo1(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 split_hi4(const float4& t) { return t; }
+__device__ __forceinline__ float4 split_lo4(const float4& t, const float4&) {
+    return make_float4(split_lo1(t.x), split_lo1(t.y), split_lo1(t.z), split_lo1(t.w));
+}
+#else
+__device__ __forceinline__ float4 split_hi4(const float4& t) { return make_float4(tf32_hi(t.x), tf32_hi(t.y), tf32_hi(t.z), tf32_hi(t.w)); }
+__device__ __forceinline__ float4 split_lo4(const float4& t, const float4& hi) {
+    return make_float4(tf32_hi(t.x - hi.x), tf32_hi(t.y - hi.y), tf32_hi(t.z - hi.z), tf32_hi(t.w - hi.w));
+}
+#endif
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 128-byte rows, 8-row groups 1024 bytes apart
 // same layout with an explicit stride between 8-row groups (halo patches: one image row of the patch per group)
 __device__ __forceinline__ uint64_t make_desc_sbo(uint32_t saddr, uint32_t sbo) {

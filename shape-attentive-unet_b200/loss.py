@@ -26,7 +26,7 @@ def _nhwc_logits(t):
 
 class _DualLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, seg, edge, seg_t, edge_t, class_w, parts):
+    def forward(ctx, seg, edge, seg_t, edge_t, class_w, parts, holder=None):
         if not seg.is_cuda:
             raise RuntimeError("saunet_b200 loss: CUDA tensors required; there is no CPU fallback")
         if seg.dtype != torch.float32:
@@ -47,10 +47,15 @@ class _DualLossFn(torch.autograd.Function):
         else:
             edge_c = edge_tc = None
         acc = torch.zeros(2 + 2 * C + 1, dtype=torch.float64, device=dev)
-        out = torch.empty(4, dtype=torch.float32, device=dev)
+        out = torch.empty(4 + 8, dtype=torch.float32, device=dev)
+        counts = torch.zeros(2 + 3 * 7 + 1, dtype=torch.int32, device=dev) if holder is not None else None
         _C.call("saunet_dual_loss_fwd", logits.data_ptr(), C, edge_c.data_ptr() if edge_c is not None else None,
                 seg_t.data_ptr(), edge_tc.data_ptr() if edge_tc is not None else None, npix, C,
-                class_w.data_ptr() if class_w is not None else None, parts, acc.data_ptr(), out.data_ptr(), st)
+                class_w.data_ptr() if class_w is not None else None, parts, acc.data_ptr(), out.data_ptr(),
+                counts.data_ptr() if counts is not None else None, st)
+        if holder is not None:
+            # SegmentationModule's metrics (models/models.py:51-74,92) counted by the same pass
+            holder["metrics"] = ((seg.data_ptr(), tuple(seg.shape)), out, counts, C)
         ctx.saved = (logits, edge_c, seg_t, edge_tc, class_w, acc)
         ctx.meta = (B, C, H, W, parts, edge.shape if edge is not None else None)
         ctx.parts_out = out
@@ -71,7 +76,7 @@ class _DualLossFn(torch.autograd.Function):
                 class_w.data_ptr() if class_w is not None else None, acc.data_ptr(), gl.data_ptr(), dlogits.data_ptr(),
                 C, dedge.data_ptr() if dedge is not None else None, parts, st)
         dseg = dlogits.view(B, H, W, C).permute(0, 3, 1, 2)
-        return dseg, (dedge.view(eshape) if dedge is not None else None), None, None, None, None
+        return dseg, (dedge.view(eshape) if dedge is not None else None), None, None, None, None, None
 
 
 def dice_loss(true, logits, eps=1e-7):
@@ -93,6 +98,7 @@ class DualLoss(nn.Module):
         self.register_buffer("class_weight", torch.tensor([1.0, 4.0, 5.0, 1.0]), persistent=False)
         self.epoch = 1
         self.alpha = 1.0
+        self._holder = {}
 
     def forward(self, pred, target, epoch=0):
         seg, edge_in = pred
@@ -103,7 +109,22 @@ class DualLoss(nn.Module):
         if w.device != seg.device:
             w = w.to(seg.device)
             self.class_weight = w
-        return _DualLossFn.apply(seg, edge_in, seg_t, edge_t, w, _PART_DICE | _PART_CE | _PART_BCE)
+        self._holder = {}
+        return _DualLossFn.apply(seg, edge_in, seg_t, edge_t, w, _PART_DICE | _PART_CE | _PART_BCE, self._holder)
+
+    def fused_metrics(self, seg):
+        """(acc, [jaccard_1 .. jaccard_{C-1}]) of models/models.py:51-74 for the logits of the LAST forward call, as
+        0-d device tensors, counted inside the loss kernel; None if ``seg`` is not the tensor that call saw."""
+        m = self._holder.get("metrics")
+        if m is None or m[0] != (seg.data_ptr(), tuple(seg.shape)):
+            return None
+        _, out, _, C = m
+        return out[4], [out[4 + i] for i in range(1, C)]
+
+    def invalid_label_count(self):
+        """Number of target labels outside [0, C) in the last forward (skipped by every sum); a device tensor."""
+        m = self._holder.get("metrics")
+        return None if m is None else m[2][2 + 3 * 7]
 
 
 DiceLoss = dice_loss

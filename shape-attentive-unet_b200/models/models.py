@@ -65,9 +65,14 @@ class SegmentationModule(SegmentationModuleBase):
         if segSize is None:          # training
             p = self.unet(feed_dict["image"])
             loss = self.crit(p, feed_dict["mask"], epoch=epoch)
-            label = feed_dict["mask"][0].long().to(p[0].device)
-            acc = self.pixel_acc(torch.round(nn.functional.softmax(p[0].detach(), dim=1)).long(), label,
-                                 self.num_class)
+            # metrics (models/models.py:92): counted by the loss kernel's own pass over the logits when `crit` is this
+            # repo's DualLoss; any other criterion takes the reference's torch expression
+            fm = getattr(self.crit, "fused_metrics", None)
+            acc = fm(p[0]) if fm is not None and self.num_class == p[0].shape[1] else None
+            if acc is None:
+                label = feed_dict["mask"][0].long().to(p[0].device)
+                acc = self.pixel_acc(torch.round(nn.functional.softmax(p[0].detach(), dim=1)).long(), label,
+                                     self.num_class)
             return loss, acc
         if segSize is True:          # test
             maps = None
@@ -195,12 +200,18 @@ class SAUNet(nn.Module):
         Cin0, KH0, KW0 = w0.shape[1], w0.shape[2], w0.shape[3]
         pad_c = (-Cin0) % 4
         if pad_c:
+            # ONE persistent padded copy, refreshed IN PLACE whenever conv0.weight moved (version / optimizer-step
+            # generation) and on every forward recorded into a CUDA graph (so the refresh is part of the graph and the
+            # graph never reads a freed buffer)
             ent = getattr(self, "_conv0_padded", None)
-            if ent is None or ent[0] != w0._version or ent[1] != w0.data_ptr():
-                w0p = torch.zeros(C0, Cin0 + pad_c, KH0, KW0, dtype=w0.dtype, device=w0.device)
-                w0p[:, :Cin0].copy_(w0.detach())
-                ent = (w0._version, w0.data_ptr(), w0p)
+            if ent is None or ent[1] != w0.data_ptr() or ent[2].device != w0.device:
+                ent = [None, w0.data_ptr(), torch.zeros(C0, Cin0 + pad_c, KH0, KW0, dtype=w0.dtype, device=w0.device)]
                 self._conv0_padded = ent
+            gen = engine.weight_generation(w0)
+            if ent[0] != gen or engine.FORCE_PACK:
+                with torch.no_grad():
+                    ent[2][:, :Cin0].copy_(w0)
+                ent[0] = gen
             w0p = ent[2]
             xin = tp.new(B, H, W, Cin0 + pad_c)
             xin.s.t.zero_()

@@ -69,7 +69,7 @@ SIGNATURES = {
     "saunet_copy_slice": [_P, _I, _P, _I, _I, _L, _I, _P],
     "saunet_nchw_to_nhwc": [_P, _P, _I, _I, _I, _L, _P],
     "saunet_nhwc_to_nchw": [_P, _I, _P, _I, _I, _L, _P],
-    "saunet_dual_loss_fwd": [_P, _I, _P, _P, _P, _L, _I, _P, _I, _P, _P, _P],
+    "saunet_dual_loss_fwd": [_P, _I, _P, _P, _P, _L, _I, _P, _I, _P, _P, _P, _P],
     "saunet_dual_loss_bwd": [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _I, _P],
     "saunet_canny_fwd": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],
 }

@@ -186,30 +186,74 @@ class Tape:
 
 
 # ---------------------------------------------------------------------------
-# weight packing cache: (id(param), mode) -> (version, data_ptr, packed tensor)
+# weight packing cache: (id(param), mode) -> [version, data_ptr, packed tensor, weakref, repacked-in-this-capture, generation]
+#
+# Validity = (tensor._version, _GEN).  `_version` catches in-place updates made through the tensor itself
+# (optimizer.step() of torch.optim, load_state_dict, p.mul_()); it does NOT move for writes through `p.data`
+# (e.g. the reference's radam.py: `p.data.copy_(p_data_fp32)`), so every optimizer step -- of ANY
+# torch.optim.Optimizer subclass, via a global post-step hook -- also bumps the generation counter `_GEN`.
+# Code that writes weights through `.data` outside an optimizer must call `invalidate_packed()` itself.
+# A stale entry is re-packed IN PLACE: a captured CUDA graph keeps reading the buffer address it saw at capture.
 _PACK = {}
+_GEN = 0
 FORCE_PACK = False      # set while a CUDA graph is being captured: pack kernels must be part of the graph
+
+
+def invalidate_packed():
+    """Mark every cached packed / tiled weight image stale (they are rebuilt, in place, on next use)."""
+    global _GEN
+    _GEN += 1
+
+
+def _optimizer_step_hook(optimizer, args, kwargs):
+    invalidate_packed()
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(_optimizer_step_hook)
+except ImportError:            # very old torch: callers must invalidate by hand
+    pass
+
+
+def weight_generation(w):
+    return (w._version, _GEN)
+
+
+def _cache_lookup(tp, key, w, numel, repack):
+    """Shared cache protocol -> packed tensor.  `repack(dst_ptr)` enqueues the pack kernel(s) into dst."""
+    ent = _PACK.get(key)
+    if ent is not None and ent[3]() is w and ent[1] == w.data_ptr() and ent[2].numel() == numel:
+        fresh = ent[0] == w._version and ent[5] == _GEN
+        if (FORCE_PACK and not ent[4]) or not (fresh or FORCE_PACK):
+            repack(ent[2].data_ptr())           # in place: the address is what a captured graph reads
+            ent[0], ent[5] = w._version, _GEN
+            if FORCE_PACK:
+                ent[4] = True
+                tp.repacked.append(ent)
+        return ent[2]
+    out = torch.empty(numel, dtype=torch.float32, device=w.device)
+    repack(out.data_ptr())
+    _PACK[key] = [w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)), False, _GEN]
+    return out
+
+
+def reset_capture_flags():
+    """Clear the repacked-during-capture marks (GraphedStep calls this in a finally: a capture that recorded a
+    forward without its backward must not leave entries flagged)."""
+    for ent in _PACK.values():
+        ent[4] = False
 
 
 def packed(tp, w, mode, A=None, Bc=None):
     """Packed GEMM layout of a conv / conv-transpose weight (see saunet_pack_weights)."""
-    key = (id(w), mode)
-    ent = _PACK.get(key)
-    if ent is not None and ent[3]() is w and ent[1] == w.data_ptr() and (ent[0] == w._version or FORCE_PACK):
-        if FORCE_PACK and not ent[4]:
-            # re-pack in place into the cached buffer (its address is what later launches of the graph read)
-            a, b, kh, kw = w.shape
-            _C.call("saunet_pack_weights", w.data_ptr(), ent[2].data_ptr(), a, b, kh, kw, mode, tp.stream)
-            ent[4] = True
-            tp.repacked.append(ent)
-        return ent[2].data_ptr()
     if not w.is_contiguous():
         raise RuntimeError("saunet_b200: conv weights must be contiguous")
     a, b, kh, kw = w.shape
-    out = torch.empty(w.numel(), dtype=torch.float32, device=w.device)
-    _C.call("saunet_pack_weights", w.data_ptr(), out.data_ptr(), a, b, kh, kw, mode, tp.stream)
-    _PACK[key] = [w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)), False]
-    return out.data_ptr()
+
+    def repack(dst):
+        _C.call("saunet_pack_weights", w.data_ptr(), dst, a, b, kh, kw, mode, tp.stream)
+    return _cache_lookup(tp, (id(w), mode), w, w.numel(), repack).data_ptr()
 
 
 # ---------------------------------------------------------------------------
@@ -218,6 +262,7 @@ def packed(tp, w, mode, A=None, Bc=None):
 #   "3xtf32" tcgen05 tensor cores, hi/lo tf32 split of both operands, fp32 accumulate in TMEM (fp32-class accuracy)
 #   "tf32"   tcgen05, single pass (what cuDNN does by default for PyTorch convs); ~1e-3 relative error
 _PRECISION = os.environ.get("SAUNET_PRECISION", "3xtf32")
+_WIDE_TILES = os.environ.get("SAUNET_WIDE_TILES", "1") == "1"
 
 
 def set_precision(name):
@@ -244,24 +289,16 @@ def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None):
         # persistent kernels: a 128-wide tile runs at ~2x the efficiency of the narrow ones (MMA operand traffic vs
         # math balance at N = 128), so keep it as long as most SMs get a tile; only really small problems trade tile
         # width for CTA count
-        floor = 96 if bn >= 128 and os.environ.get("SAUNET_WIDE_TILES", "1") == "1" else 148
+        floor = 96 if bn >= 128 and _WIDE_TILES else 148
         while bn > 32 and mt * ((N + bn - 1) // bn) < floor:
             bn //= 2
             floor = 148
-    key = (id(w), mode, phase, bn, passes)
-    ent = _PACK.get(key)
     K = taps * Cin
-    if ent is not None and ent[3]() is w and ent[1] == w.data_ptr() and (ent[0] == w._version or FORCE_PACK):
-        if FORCE_PACK and not ent[4]:
-            kn = packed(tp, w, mode) + 4 * phase * K * N
-            _C.call("saunet_pack_weights_tc", kn, taps, Cin, N, bn, passes, ent[2].data_ptr(), tp.stream)
-            ent[4] = True
-            tp.repacked.append(ent)
-        return ent[2].data_ptr(), bn, passes
-    kn = packed(tp, w, mode) + 4 * phase * K * N
-    out = torch.empty(lib.saunet_tc_packed_floats(K, N, bn, passes), dtype=torch.float32, device=w.device)
-    _C.call("saunet_pack_weights_tc", kn, taps, Cin, N, bn, passes, out.data_ptr(), tp.stream)
-    _PACK[key] = [w._version, w.data_ptr(), out, weakref.ref(w, lambda _r, k=key: _PACK.pop(k, None)), False]
+
+    def repack(dst):
+        kn = packed(tp, w, mode) + 4 * phase * K * N
+        _C.call("saunet_pack_weights_tc", kn, taps, Cin, N, bn, passes, dst, tp.stream)
+    out = _cache_lookup(tp, (id(w), mode, phase, bn, passes), w, lib.saunet_tc_packed_floats(K, N, bn, passes), repack)
     return out.data_ptr(), bn, passes
 
 
@@ -550,6 +587,8 @@ class _TapeFn(torch.autograd.Function):
         if tp is None:
             raise RuntimeError("saunet_b200: backward through a forward that did not record a tape")
         tp.stream = torch.cuda.current_stream(tp.device).cuda_stream
+        if tp.arena is not None:
+            tp.arena.ensure_attached()      # zero_grad(set_to_none=True) detached the p.grad views: zero + re-attach
         for o, g in zip(ctx.outs, gouts):
             if g is None:
                 continue
@@ -583,4 +622,15 @@ def run(module, body, inputs):
             raise RuntimeError("saunet_b200: input tensors must be CUDA tensors; there is no CPU fallback")
     # (grad mode is off inside Function.forward, so decide here whether a backward tape is needed)
     record = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or any(t.requires_grad for t in inputs))
-    return _TapeFn.apply(body, getattr(module, "_saunet_grad_arena", None), record, len(inputs), *inputs, *params)
+    arena = getattr(module, "_saunet_grad_arena", None)
+    if arena is not None and record:
+        # Gradients land in the flat arena (p.grad are views of it), so autograd needs no edge to the ~700 parameters:
+        # a fresh zero-size leaf carries "requires grad" instead.  Besides sparing autograd 700 AccumulateGrad nodes
+        # per step, this keeps CUDA-graph capture safe: a parameter's AccumulateGrad node is pinned to the stream of
+        # the first graph that used it and survives as long as any earlier loss tensor is alive -- capturing a
+        # backward through it then fails with cudaErrorStreamCaptureIsolation.
+        anchor = torch.empty(0, dtype=torch.float32, device=inputs[0].device, requires_grad=True)
+        extra = [anchor] + [p for p in params if p.requires_grad and arena.ptr(p) is None]
+    else:
+        extra = params
+    return _TapeFn.apply(body, arena, record, len(inputs), *inputs, *extra)

@@ -34,6 +34,7 @@ class GraphedStep:
                 self.loss, self.acc = self._eager(epoch)
         finally:
             engine.FORCE_PACK = False
+            engine.reset_capture_flags()
 
     def _eager(self, epoch):
         s = self.static

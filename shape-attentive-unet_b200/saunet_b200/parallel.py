@@ -56,9 +56,11 @@ class GradArena:
                 arr[i].first, arr[i].packed_off, arr[i].grad_off, arr[i].A, arr[i].Bc, arr[i].T = e
             raw = bytes(arr)
             self._unpack_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._views = {}
         for p in params:
             o = self.offsets[id(p)]
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
+            self._views[id(p)] = self.flat[o:o + p.numel()].view_as(p)
+            p.grad = self._views[id(p)]
         n = max(1, int(bucket_mb * (1 << 20) // 4))
         self.buckets = [self.flat[i:i + n] for i in range(0, self.n_grad, n)]
         module._saunet_grad_arena = self
@@ -81,6 +83,23 @@ class GradArena:
 
     def zero(self):
         self.flat.zero_()          # (the packed images are cleared by the unpack kernel as it consumes them)
+        self.attach()
+
+    def attach(self):
+        """(Re-)install the arena views as ``p.grad``."""
+        for p in self.params:
+            v = self._views[id(p)]
+            if p.grad is not v:
+                p.grad = v
+
+    def ensure_attached(self):
+        """Called at the start of every backward.  ``module.zero_grad()`` / ``optimizer.zero_grad()`` default to
+        set_to_none=True (train.py:93 of the reference calls the former every iteration): ``p.grad`` is then None while
+        the kernels keep accumulating into the arena, and optimizer.step() would silently skip every parameter.  A
+        detached view therefore means "the gradients were just reset": zero the arena and re-attach the views."""
+        if any(p.grad is not self._views[id(p)] for p in self.params):
+            self.flat.zero_()
+            self.attach()
 
     def all_reduce(self, group=None):
         """SUM-reduce in place and scale by 1/world (mean over ranks)."""

@@ -110,6 +110,74 @@ def test_grad_arena_packed_table_layout():
     assert float(arena.flat.abs().sum()) == 0.0 and float(arena.packed.min()) == 1.0     # zero() leaves the (self-clearing) images alone
 
 
+class _DataSGD(torch.optim.Optimizer):
+    """writes through p.data like the reference's radam.py:76 (no version bump)"""
+
+    def __init__(self, params):
+        super().__init__(params, dict(lr=0.1))
+
+    def step(self, closure=None):
+        for gr in self.param_groups:
+            for p in gr["params"]:
+                p.data.copy_(p.data * 0.5)
+
+
+def test_pack_cache_follows_data_writes(monkeypatch):
+    """`p.data.copy_()` does not bump `_version`; the packed-weight cache must still go stale after an
+    optimizer step (global post-step hook -> generation counter) and re-pack IN PLACE (a captured CUDA graph keeps
+    reading the old address).  Host logic only: the pack kernel is replaced by a recorder."""
+    from saunet_b200 import _C, engine
+    calls = []
+    monkeypatch.setattr(_C, "call", lambda name, *a, **k: calls.append((name, a)))
+
+    class TP:
+        stream = 0
+        repacked = []
+    w = torch.nn.Parameter(torch.randn(8, 4, 3, 3))
+    p0 = engine.packed(TP, w, 0)
+    assert len(calls) == 1 and engine.packed(TP, w, 0) == p0 and len(calls) == 1          # cached
+    v = w._version
+    opt = _DataSGD([w])
+    opt.step()
+    assert w._version == v                                                                  # the trap
+    assert engine.packed(TP, w, 0) == p0 and len(calls) == 2                                # stale -> re-packed, same buffer
+    with torch.no_grad():
+        w.mul_(2.0)                                                                         # version bump path
+    assert engine.packed(TP, w, 0) == p0 and len(calls) == 3
+    w.data.mul_(2.0)
+    assert engine.packed(TP, w, 0) == p0 and len(calls) == 3                                # undetectable without a hint ...
+    engine.invalidate_packed()
+    assert engine.packed(TP, w, 0) == p0 and len(calls) == 4                                # ... which the API provides
+    engine.FORCE_PACK = True
+    try:
+        tp = TP()
+        tp.repacked = []
+        assert engine.packed(tp, w, 0) == p0 and len(calls) == 5 and len(tp.repacked) == 1  # graph capture: always, once
+        assert engine.packed(tp, w, 0) == p0 and len(calls) == 5
+    finally:
+        engine.FORCE_PACK = False
+        engine.reset_capture_flags()
+    assert all(not e[4] for e in engine._PACK.values())
+
+
+def test_grad_arena_survives_zero_grad_set_to_none():
+    """train.py:93 calls module.zero_grad() (set_to_none=True): the arena views must come back (and
+    the arena must be cleared) before the backward kernels accumulate, or optimizer.step() skips every parameter."""
+    from saunet_b200.parallel import GradArena
+    m = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.BatchNorm2d(8))
+    arena = GradArena(m)
+    arena.flat.fill_(3.0)
+    m.zero_grad()
+    assert all(p.grad is None for p in m.parameters())
+    arena.ensure_attached()
+    assert float(arena.flat.abs().sum()) == 0.0
+    for p in m.parameters():
+        assert p.grad is not None and p.grad.data_ptr() == arena.ptr(p)
+    arena.flat.fill_(2.0)
+    arena.ensure_attached()                      # nothing detached: gradients are left to accumulate
+    assert float(arena.flat.min()) == 2.0
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the reference algorithm on the host CPU, the one place outside tests/ and smoke()
     that executes oracle/): one JSON line with the keys the driver reads, no GPU needed."""

@@ -63,6 +63,35 @@ def test_train_step_grads_and_bn_buffers():
             assert rel_err(r["bn_updates"][k[3:]], g[k]) < 1e-5, k
 
 
+def test_maps_and_metrics_match_reference():
+    """return_att maps (models/models.py:386-393) and SegmentationModule's pixel accuracy / Jaccard (:51-74,92)."""
+    g = load_golden("saunet_maps_b2_s64")
+    data = synth.synthetic_batch(2, 64, seed=304)
+    r = O.train_step(_weights(), data["image"], data["seg"], data["edge"], return_att=True)
+    assert rel_err(r["logits"], g["logits"]) < 2e-5
+    assert len(r["maps"]) == 7
+    for i, t in enumerate(r["maps"]):
+        assert t.shape == (2, 1, 64, 64) and rel_err(t, g["map%d" % i]) < 2e-5, i
+    acc, jac = O.pixel_metrics(r["logits"], data["seg"], 4)
+    assert abs(float(acc) - float(g["acc"])) < 1e-6
+    assert np.allclose([float(j) for j in jac], g["jaccard"], atol=1e-6)
+
+
+def test_b16_fixture_is_the_headline_config():
+    """tests/golden/saunet_train_b16_s256.npz = BASELINE configs[1] (batch 16, 256x256, train mode) minted from the real
+    reference; here only its bookkeeping is checked (the oracle needs ~25 s per step at this size: the GPU test
+    compares the CUDA path with it directly)."""
+    g = load_golden("saunet_train_b16_s256")
+    assert g["logits"].shape == (16, 4, 32, 32) and int(g["probe_stride"]) == 8
+    assert all(("map%d" % i) in g and g["map%d" % i].shape == (16, 1, 32, 32) for i in range(7))
+    assert len(g["grad_names"]) > 500 and g["jaccard"].shape == (3,)
+    data = synth.synthetic_batch(16, 256, seed=304)
+    assert abs(float(data["image"].double().sum()) - float(g["image_sum"])) < 1e-3
+    assert int(data["seg"].sum()) == int(g["seg_sum"]) and float(data["edge"].sum()) == float(g["edge_sum"])
+    acc, jac = O.pixel_metrics(torch.from_numpy(g["logits"]), data["seg"][:, ::8, ::8], 4)   # probes only: sanity, not parity
+    assert 0.0 <= float(acc) <= 1.0
+
+
 def test_loss_matches_reference():
     g = load_golden("loss_dual")
     seg = torch.from_numpy(g["seg"]).requires_grad_(True)
