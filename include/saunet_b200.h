@@ -73,6 +73,9 @@ typedef struct saunet_conv_desc {
      * (fp32-class accuracy), 1 = single-pass TF32.  NULL w_tc (or an ineligible geometry: Cin % 4 != 0, unaligned
      * x) selects the exact-fp32 FFMA kernel, which reads `w`. */
     const float* w_tc; int tc_bn; int tc_passes;
+    /* 1: w_tc is the chunk-major PADDED image of saunet_pack_weights_tc_cm (k-blocks = (32-channel chunk, tap), last
+     * chunk zero-padded): what the TMA-fed 3x3 kernel (conv_halo_tma.cu) reads when Cin % 32 != 0 */
+    int tc_cm;
 } saunet_conv_desc;
 
 int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream);
@@ -104,6 +107,8 @@ int saunet_tc_tile_n(int Cout);
 long long saunet_tc_packed_floats(int K, int N, int BN, int passes);
 int saunet_tc_chunk_major(int taps, int Cin);   /* 1: K-blocks ordered (32-channel chunk, tap) for L1 reuse across taps */
 int saunet_pack_weights_tc(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream);
+long long saunet_tc_packed_floats_cm(int taps, int Cin, int N, int BN, int passes);
+int saunet_pack_weights_tc_cm(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream);
 int saunet_unpack_wgrad(const float* packed, float* wgrad, int A, int Bc, int KH, int KW, int accumulate, void* stream);
 /* the same for every conv weight of a model in one launch (flat gradient arena, saunet_b200.parallel.GradArena):
  * grad_base[grad_off + ((a*Bc + b)*T + t)] += packed_base[packed_off + ((t*Bc + b)*A + a)], then that packed

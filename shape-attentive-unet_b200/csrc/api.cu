@@ -31,6 +31,8 @@ bool conv_wgrad_halo_eligible(const saunet_wgrad_desc* d);
 int conv_wgrad_pw(const saunet_wgrad_desc* d, cudaStream_t st);
 bool conv_wgrad_pw_eligible(const saunet_wgrad_desc* d);
 int conv_fwd_pw_t(const saunet_conv_desc* d, cudaStream_t st);
+int conv_fwd_halo_tma(const saunet_conv_desc* d, cudaStream_t st);
+bool conv_halo_tma_eligible(const saunet_conv_desc* d);
 bool conv_pw_t_eligible(const saunet_conv_desc* d);
 }  // namespace saunet
 
@@ -53,6 +55,8 @@ extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
     SAUNET_CHECK_ARG((d->stat_sum == nullptr) == (d->stat_sumsq == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: stat_sum/stat_sumsq mismatch");
     SAUNET_CHECK_ARG(d->act >= 0 && d->act <= 2, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: bad activation %d", d->act);
     if (conv_skinny_eligible(d)) return conv_fwd_skinny(d, (cudaStream_t)stream);
+    if (conv_halo_tma_eligible(d)) return conv_fwd_halo_tma(d, (cudaStream_t)stream);      // 3x3: TMA-fed persistent halo kernel
+    SAUNET_CHECK_ARG(!d->tc_cm, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: chunk-major padded weights (tc_cm) given for a geometry the TMA halo kernel does not take");
     if (conv_halo_eligible(d) && !SAUNET_ENV_FLAG("SAUNET_NO_HALO")) return conv_fwd_halo(d, (cudaStream_t)stream);
     if (conv_pw_t_eligible(d)) return conv_fwd_pw_t(d, (cudaStream_t)stream);      // large 1x1 layers: channels on the TMEM lanes
     if (conv_tc_eligible(d)) return conv_fwd_tc(d, (cudaStream_t)stream);

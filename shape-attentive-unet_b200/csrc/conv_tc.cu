@@ -440,9 +440,13 @@ __global__ void pack_tc_kernel(const float* __restrict__ kn, int K, int N, int B
         const int nt = (int)r;
         const int lc = pc ^ (row & 7);                // logical chunk
         int k = kb * 32 + lc * 4 + e;
-        if (chunk_major) { const int cc = kb / taps, tap = kb - cc * taps; k = tap * Cin + cc * 32 + lc * 4 + e; }
+        bool kval = k < K;
+        if (chunk_major) {          // (chunk, tap) order; a partial last chunk (Cin % 32 != 0, padded image) is zero-filled
+            const int cc = kb / taps, tap = kb - cc * taps, cch = cc * 32 + lc * 4 + e;
+            k = tap * Cin + cch; kval = cch < Cin;
+        }
         const int n = nt * BN + row;
-        float w = (k < K && n < N) ? kn[(size_t)k * N + n] : 0.f;
+        float w = (kval && n < N) ? kn[(size_t)k * N + n] : 0.f;
         float hi = tf32_hi(w);
         out[idx] = (op == 0) ? hi : tf32_hi(w - hi);
     }
@@ -516,6 +520,22 @@ extern "C" int saunet_tc_tile_n(int Cout) {
     if (Cout <= 32) return 32;
     if (Cout <= 64) return 64;
     return 128;        // (a 256-wide tile leaves no shared memory for the output staging tile of the bulk-copy epilogue)
+}
+// chunk-major PADDED image (conv_halo_tma.cu): k-blocks ordered (32-channel chunk, tap), the last chunk zero-padded
+extern "C" long long saunet_tc_packed_floats_cm(int taps, int Cin, int N, int BN, int passes) {
+    if (taps <= 0 || Cin <= 0 || N <= 0 || BN <= 0) return 0;
+    const long long nkb = (long long)((Cin + 31) / 32) * taps, ntile = (N + BN - 1) / BN;
+    return ntile * nkb * (passes == 3 ? 2 : 1) * BN * 32;
+}
+extern "C" int saunet_pack_weights_tc_cm(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream) {
+    SAUNET_CHECK_ARG(kn && out && taps > 0 && Cin > 0 && N > 0, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc_cm: bad args");
+    SAUNET_CHECK_ARG(BN == 16 || BN == 32 || BN == 64 || BN == 128, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc_cm: bad N tile %d", BN);
+    SAUNET_CHECK_ARG(passes == 1 || passes == 3, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc_cm: passes must be 1 or 3");
+    const long long total = saunet_tc_packed_floats_cm(taps, Cin, N, BN, passes);
+    int blocks = (int)((total + 255) / 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kn, taps * Cin, N, BN, passes, ((Cin + 31) / 32) * taps, taps, Cin, 1, out);
+    SAUNET_CHECK_LAUNCH("pack_tc_kernel");
+    return SAUNET_OK;
 }
 extern "C" long long saunet_tc_packed_floats(int K, int N, int BN, int passes) {
     if (K <= 0 || N <= 0 || BN <= 0) return 0;

@@ -22,7 +22,7 @@ class ConvDesc(Structure):
                 ("in_scale", c_void_p), ("in_shift", c_void_p), ("in_relu", c_int),
                 ("bias", c_void_p), ("row_scale", c_void_p), ("row_scale_add", c_float),
                 ("act", c_int), ("accumulate", c_int), ("stat_sum", c_void_p), ("stat_sumsq", c_void_p),
-                ("w_tc", c_void_p), ("tc_bn", c_int), ("tc_passes", c_int)]
+                ("w_tc", c_void_p), ("tc_bn", c_int), ("tc_passes", c_int), ("tc_cm", c_int)]
 
 
 class WgradDesc(Structure):
@@ -48,6 +48,7 @@ SIGNATURES = {
     "saunet_unpack_wgrad": [_P, _P, _I, _I, _I, _I, _I, _P],
     "saunet_unpack_wgrad_multi": [_P, _I, _L, _P, _P, _P],
     "saunet_pack_weights_tc": [_P, _I, _I, _I, _I, _I, _P, _P],
+    "saunet_pack_weights_tc_cm": [_P, _I, _I, _I, _I, _I, _P, _P],
     "saunet_channel_stats": [_P, _I, _I, _L, _P, _P, _P],
     "saunet_add_d2f": [_P, _P, _I, _P],
     "saunet_bn_finalize": [_P, _P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P],
@@ -82,6 +83,7 @@ _SPECIAL = {
     "saunet_tc_tile_n": ([_I], c_int),
     "saunet_tc_chunk_major": ([_I, _I], c_int),
     "saunet_tc_packed_floats": ([_I, _I, _I, _I], c_longlong),
+    "saunet_tc_packed_floats_cm": ([_I, _I, _I, _I, _I], c_longlong),
 }
 ALL_SYMBOLS = sorted(list(SIGNATURES) + list(_SPECIAL))
 

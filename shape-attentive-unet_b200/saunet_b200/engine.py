@@ -276,7 +276,7 @@ def get_precision():
     return _PRECISION
 
 
-def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None):
+def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None, cm=False):
     """Tensor-core tiling of a packed [K][N] weight (see saunet_pack_weights_tc) -> (ptr, BN, passes) or None.
     M (GEMM rows) lets small problems take a narrower N tile so that at least ~one CTA per SM exists."""
     if _PRECISION == "fp32":
@@ -297,9 +297,16 @@ def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None):
 
     def repack(dst):
         kn = packed(tp, w, mode) + 4 * phase * K * N
-        _C.call("saunet_pack_weights_tc", kn, taps, Cin, N, bn, passes, dst, tp.stream)
-    out = _cache_lookup(tp, (id(w), mode, phase, bn, passes), w, lib.saunet_tc_packed_floats(K, N, bn, passes), repack)
-    return out.data_ptr(), bn, passes
+        _C.call("saunet_pack_weights_tc_cm" if cm else "saunet_pack_weights_tc", kn, taps, Cin, N, bn, passes, dst, tp.stream)
+    numel = lib.saunet_tc_packed_floats_cm(taps, Cin, N, bn, passes) if cm else lib.saunet_tc_packed_floats(K, N, bn, passes)
+    out = _cache_lookup(tp, (id(w), mode, phase, bn, passes, cm), w, numel, repack)
+    return out.data_ptr(), bn, passes, 1 if cm else 0
+
+
+def _wants_cm(x, KH, KW, stride, pad):
+    """Mirror of conv_halo_tma_eligible (csrc/conv_halo_tma.cu) for channel counts that are not a multiple of 32: those
+    3x3 layers (res3: 16 channels, dec1: 48) reach the TMA-fed kernel through the chunk-major padded weight image."""
+    return KH == 3 and KW == 3 and stride == 1 and pad == 1 and x.H % 16 == 0 and x.W % 8 == 0 and x.C % 32 != 0
 
 
 def _tc_ok(x, Cout, K):
@@ -331,9 +338,10 @@ def conv(tp, x, wptr, Cout, KH, KW, y, Hg, Wg, sy=1, sx=1, offy=0, offx=0, osy=1
     else:
         d.stat_sum, d.stat_sumsq = None, None
     if wtc is not None:
-        d.w_tc, d.tc_bn, d.tc_passes = wtc
+        d.w_tc, d.tc_bn, d.tc_passes = wtc[:3]
+        d.tc_cm = wtc[3] if len(wtc) > 3 else 0
     else:
-        d.w_tc, d.tc_bn, d.tc_passes = None, 0, 0
+        d.w_tc, d.tc_bn, d.tc_passes, d.tc_cm = None, 0, 0, 0
     M = x.B * Hg * Wg
     _C.call("saunet_conv2d_fwd", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * x.C * Cout,
             nbytes=4.0 * (x.npix * x.C + M * Cout + KH * KW * x.C * Cout),
@@ -457,7 +465,8 @@ def conv2d(tp, x, w, b, y=None, stride=1, pad=0, pro=None, pro_relu=0, act=ACT_N
     K = KH * KW * Cin
     conv(tp, x, packed(tp, w, 0), Cout, KH, KW, y, Ho, Wo, sy=stride, sx=stride, offy=-pad, offx=-pad,
          pro=pro.state if pro is not None else 0, pro_relu=pro_relu, bias=_p(b), row_scale=row_scale, row_add=row_add,
-         act=act, stat=stat, wtc=packed_tc(tp, w, 0, KH * KW, Cin, Cout, M=x.B * Ho * Wo) if _tc_ok(x, Cout, K) else None)
+         act=act, stat=stat, wtc=packed_tc(tp, w, 0, KH * KW, Cin, Cout, M=x.B * Ho * Wo,
+                                           cm=_wants_cm(x, KH, KW, stride, pad)) if _tc_ok(x, Cout, K) else None)
     r = ConvRec()
     r.x, r.y, r.w, r.b, r.k, r.stride, r.pad, r.pro, r.pro_relu = x, y, w, b, (KH, KW), stride, pad, pro, pro_relu
     return y, r
@@ -482,7 +491,8 @@ def conv2d_bwd(tp, r, dy, dx=None, dx_acc=0, need_bias=True):
             raise RuntimeError("saunet_b200: data gradient of a strided conv is not on the SAUNet path")
         Kd = KH * KW * Cout
         conv(tp, dy, packed(tp, w, 1), Cin, KH, KW, dx, x.H, x.W, offy=-(KH - 1 - r.pad), offx=-(KW - 1 - r.pad),
-             acc=dx_acc, wtc=packed_tc(tp, w, 1, KH * KW, Cout, Cin, M=x.npix) if _tc_ok(dy, Cin, Kd) else None)
+             acc=dx_acc, wtc=packed_tc(tp, w, 1, KH * KW, Cout, Cin, M=x.npix,
+                                       cm=_wants_cm(dy, KH, KW, 1, r.pad)) if _tc_ok(dy, Cin, Kd) else None)
 
 
 # ---- ConvTranspose2d k4 s2 p1 (attention_blocks.py:179-183, models.py:211) as 4 output phases ----------

@@ -66,6 +66,13 @@ CASES = [
     (1, 16, 8, 32, 16, 3, 1, 1, 32, 16, True, False, True, False, ACT_NONE, 0),
     (3, 16, 40, 96, 128, 3, 1, 1, 0, 0, True, True, False, False, ACT_NONE, 1),
     (2, 48, 16, 160, 48, 3, 1, 1, 0, 0, False, False, True, False, ACT_SIGMOID, 0),
+    # ... and channel counts that are not a multiple of 32: the TMA unit zero-fills the K padding (conv_halo_tma.cu)
+    (2, 32, 16, 16, 16, 3, 1, 1, 0, 0, True, False, True, False, ACT_NONE, 0),       # res3: 16 -> 16 with BN prologue
+    (1, 16, 24, 48, 64, 3, 1, 1, 16, 0, False, False, False, False, ACT_NONE, 1),    # dec1 dgrad: 48 -> 64, accumulate
+    (2, 16, 8, 80, 32, 3, 1, 1, 0, 32, True, True, True, False, ACT_RELU, 0),        # 2.5 chunks
+    (5, 64, 64, 32, 32, 3, 1, 1, 0, 0, False, False, True, False, ACT_NONE, 0),      # 160 tiles: persistent loop wraps, one chunk
+    (2, 64, 48, 128, 32, 3, 1, 1, 0, 0, True, False, True, False, ACT_NONE, 0),      # dense conv2, several tiles per CTA
+    (1, 32, 32, 64, 128, 3, 1, 1, 0, 0, False, True, False, False, ACT_NONE, 0),     # wide tile (two patch buffers)
     # large pointwise layers (>= 74 tiles of 256 pixels x 128 channels): also the shapes of the channels-on-lanes kernel
     # (conv_pw_t.cu)
     (2, 128, 128, 96, 128, 1, 1, 0, 32, 0, True, False, True, False, ACT_NONE, 0),   # dense conv1: prologue + statistics
@@ -98,7 +105,7 @@ def test_conv_matches_fp64(case, passes, tol):
         y = tp.new(B, Ho, Wo, Cout, ld=Cout + ye)
         y.s.t.copy_(y0)
         st = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
-        wtc = packed_tc(tp, w, 0, k * k, Cin, Cout) if use_tc else None
+        wtc = packed_tc(tp, w, 0, k * k, Cin, Cout, cm=engine._wants_cm(x, k, k, stride, pad)) if use_tc else None
         assert (wtc is not None) == use_tc
         conv(tp, x, packed(tp, w, 0), Cout, k, k, y, Ho, Wo, sy=stride, sx=stride, offy=-pad, offx=-pad,
              pro=state.data_ptr() if pro else 0, pro_relu=1 if pro else 0, bias=bvec.data_ptr() if bias else 0,

@@ -19,10 +19,12 @@ y = tp.new(B, H, W, Cout); y.s.t.normal_()
 w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
 st = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
 dw = torch.zeros(k * k * Cin * Cout, device=dev)
+pro_state = torch.cat([0.5 + torch.rand(Cin), 0.3 * torch.randn(Cin)]).to(dev) if os.environ.get('PRO') else None
 def run():
     if kind == "fwd":
         conv(tp, x, packed(tp, w, 0), Cout, k, k, y, H, W, offy=-(k // 2), offx=-(k // 2),
-             stat=None if os.environ.get('NOSTAT') else (st.data_ptr(), st.data_ptr() + 8 * Cout), wtc=packed_tc(tp, w, 0, k * k, Cin, Cout))
+             stat=None if os.environ.get('NOSTAT') else (st.data_ptr(), st.data_ptr() + 8 * Cout), wtc=packed_tc(tp, w, 0, k * k, Cin, Cout, M=B * H * W, cm=engine._wants_cm(x, k, k, 1, k // 2)),
+             pro=pro_state.data_ptr() if pro_state is not None else 0, pro_relu=1)
     else:
         wgrad(tp, y, x, dw.data_ptr(), k, k, H, W, offy=-(k // 2), offx=-(k // 2))
 for _ in range(2): run()
