@@ -76,6 +76,13 @@ typedef struct saunet_conv_desc {
     /* 1: w_tc is the chunk-major PADDED image of saunet_pack_weights_tc_cm (k-blocks = (32-channel chunk, tap), last
      * chunk zero-padded): what the TMA-fed 3x3 kernel (conv_halo_tma.cu) reads when Cin % 32 != 0 */
     int tc_cm;
+    /* fused BatchNorm(+ReLU)-backward epilogue (1x1 data gradients, conv_pw_t.cu): the GEMM result is
+     * da = d loss / d act(bn(x)) for the tensor epi_x (same pixels, channel n of epi_x <-> output channel n):
+     *   g = da * [epi_relu ? epi_scale*x + epi_shift > 0 : 1];  y (+)= epi_scale * g;
+     *   stat_sum[n] += sum g;  stat_sumsq[n] += sum g * (x - epi_mean[n])
+     * i.e. the data-dependent term of the BatchNorm gradient; the mean terms follow from the sums
+     * (saunet_bn_fused_finish, saunet_bn_fixup).  NULL epi_x = plain epilogue. */
+    const float* epi_x; int epi_x_ld; const float* epi_scale; const float* epi_shift; const float* epi_mean; int epi_relu;
 } saunet_conv_desc;
 
 int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream);
@@ -146,6 +153,20 @@ int saunet_bn_bwd_apply(const float* dy, int dy_ld, const float* x, int x_ld, co
                         const float* state, const float* gamma, const double* red, int C, long long npix, int act,
                         int training, float* dx, int dx_ld, int dx_acc, float* dres, int dres_ld, int dres_acc,
                         float* dgamma, float* dbeta, void* stream);
+
+/* Fused BatchNorm backward, second half (first half = the epi_x epilogue of saunet_conv2d_fwd): from
+ * sums[0][c] = sum g, sums[1][c] = sum g*(x-mean) of ONE BatchNorm application over channels [0,C):
+ *   dbeta[c] += sum g;  dgamma[c] += invstd*sum g(x-mean);
+ *   training: ab[0][c] += scale*(sum g)/n - B*mean,  ab[1][c] += B,  B = scale*invstd^2*sum g(x-mean)/n
+ * so that the complete input gradient is  dx = (sum over applications of scale*g)  -  (ab[0][c] + ab[1][c]*x).
+ * DenseNet: a feature channel feeds the norm1 of EVERY later layer (densenet.py:47-50); their ab terms add up and ONE
+ * fix-up pass per 32-channel slice replaces a reduce + an apply pass over all input channels per layer.
+ * state = [scale, shift, mean, invstd][C] (saunet_bn_finalize); ab = double[2][ab_ld]. */
+int saunet_bn_fused_finish(const double* sums, const float* state, double count, int training, int C, float* dgamma,
+                           float* dbeta, double* ab, int ab_ld, void* stream);
+/* g[p][c] -= ab[0][c] + ab[1][c] * x[p][c]   for c in [0,C)  (ab already offset to the first channel) */
+int saunet_bn_fixup(float* g, int g_ld, const float* x, int x_ld, const double* ab, int ab_ld, int C, long long npix,
+                    void* stream);
 
 /* ---- pointwise / resampling ------------------------------------------------------------------- */
 /* F.interpolate(mode='bilinear', align_corners=True) models/models.py:337-389 */

@@ -54,6 +54,13 @@ extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
     SAUNET_CHECK_ARG((d->in_scale == nullptr) == (d->in_shift == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: in_scale/in_shift mismatch");
     SAUNET_CHECK_ARG((d->stat_sum == nullptr) == (d->stat_sumsq == nullptr), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: stat_sum/stat_sumsq mismatch");
     SAUNET_CHECK_ARG(d->act >= 0 && d->act <= 2, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: bad activation %d", d->act);
+    if (d->epi_x) {
+        SAUNET_CHECK_ARG(d->epi_scale && d->epi_shift && d->epi_mean && d->epi_x_ld >= d->Cout && d->stat_sum && !d->bias && !d->row_scale &&
+                         d->act == SAUNET_ACT_NONE && conv_pw_t_eligible(d), SAUNET_ERR_BAD_SHAPE,
+                         "conv2d_fwd: the fused BatchNorm-backward epilogue needs a 1x1 / stride-1 tensor-core conv with 128-wide weight "
+                         "tiles, statistics targets, and no bias / row scale / activation");
+        return conv_fwd_pw_t(d, (cudaStream_t)stream);
+    }
     if (conv_skinny_eligible(d)) return conv_fwd_skinny(d, (cudaStream_t)stream);
     if (conv_halo_tma_eligible(d)) return conv_fwd_halo_tma(d, (cudaStream_t)stream);      // 3x3: TMA-fed persistent halo kernel
     SAUNET_CHECK_ARG(!d->tc_cm, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: chunk-major padded weights (tc_cm) given for a geometry the TMA halo kernel does not take");

@@ -39,7 +39,8 @@ struct PwtCfg {
     static constexpr int X_IMG = kTNP * 128, W_IMG = 128 * 128;
     static constexpr int STAGE = NOP * (X_IMG + W_IMG);
     static constexpr int NSTAGE = (200 * 1024) / STAGE > 4 ? 4 : (200 * 1024) / STAGE;       // 2 (3xTF32) or 4
-    static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256;
+    static constexpr int STG = 16 * 128 * 4;                   // fused BN-backward epilogue: 16 pixels x 128 channels staged per chunk
+    static constexpr int SMEM = NSTAGE * STAGE + 1024 + 256 + 4 * STG;      // (2 epilogue halves x 2 buffers)
 };
 
 template <int NPASS>
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
     auto tmem_full = [&](int b) { return bars + 8u * (3 * NSTAGE + b); };
     auto tmem_empty = [&](int b) { return bars + 8u * (3 * NSTAGE + 2 + b); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sgen + NSTAGE * Cfg::STAGE + 8 * (3 * NSTAGE + 4));
+    float* stg_base = reinterpret_cast<float*>(sgen + NSTAGE * Cfg::STAGE + 256);
     const saunet_conv_desc& d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NPW = kTProd / 32, EPI0 = NPW, MMA_WARP = NPW + kTEpi / 32, LOAD_WARP = MMA_WARP + 1;
@@ -189,6 +191,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
     } else {
         // ================= epilogue: lane = output channel, columns = pixels =================
         const int q = warp & 3, half = (warp - EPI0) >> 2;
+        int bnb_chunks = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int buf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -198,6 +201,14 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
             const int act = d.act;
             const bool has_rs = d.row_scale != nullptr, accum = d.accumulate != 0;
             float s1 = 0.f, s2 = 0.f;
+            // fused BatchNorm(+ReLU) backward epilogue (d.epi_x): this conv is the data gradient that produces
+            // da = d loss / d relu(bn(x)); per output channel co (= this thread): g = da * [scale*x + shift > 0],
+            // y (+)= scale * g (the data-dependent term of the BatchNorm gradient), stat_sum += sum g,
+            // stat_sumsq += sum g * (x - mean).  The two mean terms are applied later from those sums
+            // (saunet_bn_fused_finish / saunet_bn_fixup): `da` never goes to HBM and x is read once.
+            const bool bnb = d.epi_x != nullptr;
+            float e_sc = 0.f, e_sh = 0.f, e_mu = 0.f;
+            if (bnb && cov) { e_sc = __ldg(d.epi_scale + co); e_sh = __ldg(d.epi_shift + co); e_mu = __ldg(d.epi_mean + co); }
             mbar_wait(tmem_full(buf), tph);
             tc_fence_after();
             const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kTNP);
@@ -207,6 +218,44 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
                 float v[16];
                 tmem_ld16(tb + (uint32_t)c0, v);
                 const bool full = mc + 16 <= p.M;               // warp-uniform
+                if (bnb) {
+                    // Output staged as [16 pixels][128 channels] per (half, buffer) and sent as one bulk reduce-add (or plain
+                    // bulk store for a first writer) per pixel row, so the epilogue warps only LOAD x.  Measured on B200
+                    // (M 262144, K 128, N 224): 0.28 ms; with a register read-modify-write of y (32 loads in flight per
+                    // thread, L2-prefetched) 0.40 ms; the same GEMM writing plain da: 0.115 ms + 0.25 ms of reduce / apply passes.
+                    float* stg = stg_base + (half * 2 + (bnb_chunks++ & 1)) * (Cfg::STG / 4);      // alternate the two buffers
+                    const bool issuer = q == 0 && lane < 16;
+                    const float* xp = d.epi_x + (size_t)mc * d.epi_x_ld + co;
+                    float xv[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)                 // 16 independent 128-byte warp requests in flight
+                        xv[j] = (cov && (full || mc + j < p.M)) ? __ldg(xp + (size_t)j * d.epi_x_ld) : 0.f;
+                    if (lane < 16 && mc + 32 + lane < p.M && co - lane < d.Cout)      // pull the chunk after next into L2 meanwhile (0.38 -> 0.28 ms)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(d.epi_x + (size_t)(mc + 32 + lane) * d.epi_x_ld + (co - lane)) : "memory");
+                    if (issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");     // the buffer's previous rows have been read
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float pre = fmaf(xv[j], e_sc, e_sh);
+                        const float g = ((full || mc + j < p.M) && (!d.epi_relu || pre > 0.f)) ? v[j] : 0.f;
+                        s1 += g; s2 = fmaf(g, xv[j] - e_mu, s2);
+                        stg[j * 128 + q * 32 + lane] = e_sc * g;
+                    }
+                    fence_proxy_async();
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                    if (issuer && mc + lane < p.M) {
+                        const int n0c = (tile % p.ntile_co) * 128;
+                        const int ncols = (d.Cout - n0c) < 128 ? (d.Cout - n0c) : 128;
+                        float* dst = d.y + (size_t)(mc + lane) * d.y_ld + n0c;
+                        const uint32_t src = smem_u32(stg + lane * 128);
+                        if (accum)
+                            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(ncols * 4) : "memory");
+                        else
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(ncols * 4) : "memory");
+                    }
+                    if (issuer) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    continue;
+                }
                 float o[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
@@ -227,13 +276,16 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
                 }
                 if (cov) {
                     float* yp = d.y + (size_t)mc * d.y_ld + co;
+                    if (accum) {                                // all 16 loads first (a load-add-store chain per element ran 4x slower)
+                        float yv[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (full || mc + j < p.M) {
-                            float* q1 = yp + (size_t)j * d.y_ld;
-                            *q1 = accum ? *q1 + o[j] : o[j];
-                        }
+                        for (int j = 0; j < 16; ++j) yv[j] = (full || mc + j < p.M) ? yp[(size_t)j * d.y_ld] : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] += yv[j];
                     }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (full || mc + j < p.M) yp[(size_t)j * d.y_ld] = o[j];
                 }
             }
             tc_fence_before();
@@ -244,6 +296,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
                 atomicAdd(d.stat_sumsq + co, (double)s2);
             }
         }
+        if (d.epi_x) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -272,12 +325,13 @@ bool conv_tc_eligible(const saunet_conv_desc* d);
 
 bool conv_pw_t_eligible(const saunet_conv_desc* d) {
     static const bool off = getenv("SAUNET_CONV1X1_T") != nullptr && getenv("SAUNET_CONV1X1_T")[0] == '0';
-    if (off || !conv_tc_eligible(d) || d->tc_bn != 128) return false;
+    if ((off && !d->epi_x) || !conv_tc_eligible(d) || d->tc_bn != 128) return false;
     if (d->KH != 1 || d->KW != 1 || d->sy != 1 || d->sx != 1 || d->offy != 0 || d->offx != 0) return false;
     if (d->osy != 1 || d->osx != 1 || d->oy0 != 0 || d->ox0 != 0) return false;
     if (d->Hg != d->Hin || d->Wg != d->Win || d->Hout != d->Hin || d->Wout != d->Win) return false;
     const long long M = (long long)d->B * d->Hg * d->Wg;
     if (M >= (1ll << 31)) return false;
+    if (d->epi_x) return true;          // the fused BatchNorm-backward epilogue lives in this kernel only
     // 256-pixel tiles: keep at least ~half the SMs busy, otherwise conv_tc.cu's 128-pixel tiles spread better
     return ((M + kTNP - 1) / kTNP) * ((d->Cout + 127) / 128) >= kNumSMs / 2;
 }

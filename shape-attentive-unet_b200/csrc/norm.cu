@@ -566,6 +566,64 @@ extern "C" int saunet_bn_bwd_reduce(const float* dy, int dy_ld, const float* x, 
     return launch_reduce(o1, o4, vec, C, npix, red, (long long)C, (cudaStream_t)stream, "bn_bwd_reduce_kernel");
 }
 
+namespace saunet {
+__global__ void bn_fused_finish_kernel(const double* __restrict__ sums, const float* __restrict__ state, double inv_n, int training,
+                                       int C, float* dgamma, float* dbeta, double* ab, int ab_ld) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double s1 = sums[c], s2 = sums[C + c];
+    const double scale = state[c], mean = state[2 * C + c], istd = state[3 * C + c];
+    if (dbeta) dbeta[c] += (float)s1;
+    if (dgamma) dgamma[c] += (float)(istd * s2);
+    if (training && ab) {
+        const double B = scale * istd * istd * s2 * inv_n;
+        ab[c] += scale * s1 * inv_n - B * mean;
+        ab[ab_ld + c] += B;
+    }
+}
+
+// thread = 4 channels x strided pixels (C % 4 == 0, 16-byte aligned rows) or 1 channel
+template <int V>
+__global__ void __launch_bounds__(256) bn_fixup_kernel(float* __restrict__ g, int g_ld, const float* __restrict__ x, int x_ld,
+                                                       const double* __restrict__ ab, int ab_ld, int C, long long npix) {
+    const int L = C / V;
+    const long long total = npix * L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / L; const int c = (int)(i - p * L) * V;
+        if (V == 4) {
+            float4 gv = *reinterpret_cast<const float4*>(g + (size_t)p * g_ld + c);
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)p * x_ld + c));
+            gv.x -= (float)ab[c] + (float)ab[ab_ld + c] * xv.x;
+            gv.y -= (float)ab[c + 1] + (float)ab[ab_ld + c + 1] * xv.y;
+            gv.z -= (float)ab[c + 2] + (float)ab[ab_ld + c + 2] * xv.z;
+            gv.w -= (float)ab[c + 3] + (float)ab[ab_ld + c + 3] * xv.w;
+            *reinterpret_cast<float4*>(g + (size_t)p * g_ld + c) = gv;
+        } else {
+            g[(size_t)p * g_ld + c] -= (float)ab[c] + (float)ab[ab_ld + c] * __ldg(x + (size_t)p * x_ld + c);
+        }
+    }
+}
+}  // namespace saunet
+
+extern "C" int saunet_bn_fused_finish(const double* sums, const float* state, double count, int training, int C, float* dgamma,
+                                      float* dbeta, double* ab, int ab_ld, void* stream) {
+    SAUNET_CHECK_ARG(sums && state && C > 0 && count > 0, SAUNET_ERR_BAD_SHAPE, "bn_fused_finish: bad args");
+    SAUNET_CHECK_ARG(!training || (ab && ab_ld >= C), SAUNET_ERR_BAD_SHAPE, "bn_fused_finish: training mode needs ab[2][>=C]");
+    bn_fused_finish_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, state, 1.0 / count, training, C, dgamma, dbeta, ab, ab_ld);
+    SAUNET_CHECK_LAUNCH("bn_fused_finish_kernel");
+    return SAUNET_OK;
+}
+
+extern "C" int saunet_bn_fixup(float* g, int g_ld, const float* x, int x_ld, const double* ab, int ab_ld, int C, long long npix,
+                               void* stream) {
+    SAUNET_CHECK_ARG(g && x && ab && C > 0 && npix > 0 && g_ld >= C && x_ld >= C, SAUNET_ERR_BAD_SHAPE, "bn_fixup: bad args");
+    const bool vec = C % 4 == 0 && g_ld % 4 == 0 && x_ld % 4 == 0 && aligned16(g) && aligned16(x);
+    if (vec) bn_fixup_kernel<4><<<ew_blocks(npix * (C / 4)), 256, 0, (cudaStream_t)stream>>>(g, g_ld, x, x_ld, ab, ab_ld, C, npix);
+    else bn_fixup_kernel<1><<<ew_blocks(npix * C), 256, 0, (cudaStream_t)stream>>>(g, g_ld, x, x_ld, ab, ab_ld, C, npix);
+    SAUNET_CHECK_LAUNCH("bn_fixup_kernel");
+    return SAUNET_OK;
+}
+
 extern "C" int saunet_bn_bwd_apply(const float* dy, int dy_ld, const float* x, int x_ld, const float* out, int out_ld,
                                    const float* state, const float* gamma, const double* red, int C, long long npix, int act,
                                    int training, float* dx, int dx_ld, int dx_acc, float* dres, int dres_ld, int dres_acc,

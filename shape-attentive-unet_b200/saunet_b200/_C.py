@@ -22,7 +22,9 @@ class ConvDesc(Structure):
                 ("in_scale", c_void_p), ("in_shift", c_void_p), ("in_relu", c_int),
                 ("bias", c_void_p), ("row_scale", c_void_p), ("row_scale_add", c_float),
                 ("act", c_int), ("accumulate", c_int), ("stat_sum", c_void_p), ("stat_sumsq", c_void_p),
-                ("w_tc", c_void_p), ("tc_bn", c_int), ("tc_passes", c_int), ("tc_cm", c_int)]
+                ("w_tc", c_void_p), ("tc_bn", c_int), ("tc_passes", c_int), ("tc_cm", c_int),
+                ("epi_x", c_void_p), ("epi_x_ld", c_int), ("epi_scale", c_void_p), ("epi_shift", c_void_p),
+                ("epi_mean", c_void_p), ("epi_relu", c_int)]
 
 
 class WgradDesc(Structure):
@@ -53,6 +55,8 @@ SIGNATURES = {
     "saunet_add_d2f": [_P, _P, _I, _P],
     "saunet_bn_finalize": [_P, _P, _D, _P, _P, _P, _P, _F, _F, _I, _I, _P, _P],
     "saunet_affine_act": [_P, _I, _P, _P, _P, _I, _P, _I, _I, _L, _I, _P],
+    "saunet_bn_fused_finish": [_P, _P, _D, _I, _I, _P, _P, _P, _I, _P],
+    "saunet_bn_fixup": [_P, _I, _P, _I, _P, _I, _I, _L, _P],
     "saunet_bn_bwd_reduce": [_P, _I, _P, _I, _P, _I, _P, _I, _L, _I, _P, _P],
     "saunet_bn_bwd_apply": [_P, _I, _P, _I, _P, _I, _P, _P, _P, _I, _L, _I, _I, _P, _I, _I, _P, _I, _I, _P, _P, _P],
     "saunet_bilinear_fwd": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P],

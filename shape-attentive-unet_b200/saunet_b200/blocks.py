@@ -14,7 +14,8 @@ from torch.nn.modules.batchnorm import _BatchNorm
 
 from . import _C
 from .engine import (ACT_NONE, ACT_RELU, ACT_SIGMOID, Buf, Store, _round4, act_bwd, affine_act, bn_backward,
-                     bn_finalize, bn_stats_slot, channel_stats, conv2d, conv2d_bwd, convT4, convT4_bwd, copy_slice)
+                     bn_dgrad_fused, bn_dgrad_fused_ok, bn_finalize, bn_fixup, bn_stats_slot, channel_stats, conv2d,
+                     conv2d_bwd, convT4, convT4_bwd, copy_slice)
 
 
 def _check_bn(mod):
@@ -318,6 +319,13 @@ def dense_block_body(tp, blk, X, c_in, sums):
     n = X.npix
     B, H, W = X.B, X.H, X.W
     cin = c_in
+
+    def bwd_block_input():
+        # (registered first = runs last) BatchNorm mean terms the block's layers still owe to its input channels
+        gX = tp.grad(X)
+        if gX is not None:
+            bn_fixup(tp, gX.slice(0, c_in), X.slice(0, c_in))
+    tp.on_backward(bwd_block_input)
     for layer in blk.children():
         n1, n2 = _check_bn(layer.norm1), _check_bn(layer.norm2)
         mid, gr = layer.conv1.weight.shape[0], layer.conv2.weight.shape[0]
@@ -337,12 +345,19 @@ def dense_block_body(tp, blk, X, c_in, sums):
             gX = tp.grad(X)
             if gX is None:
                 return
+            # this layer's 32 output channels were read by the norm1 of every later layer (and the transition):
+            # settle the mean terms of those BatchNorm gradients before the slice is consumed
+            bn_fixup(tp, gX.slice(cin, gr), X.slice(cin, gr))
             da2 = tp.new(B, H, W, mid)
             conv2d_bwd(tp, r2, gX.slice(cin, gr), da2, 0)
             bn_backward(tp, bn2, da2, t1, None, ACT_RELU, da2, 0)
-            da1 = tp.new(B, H, W, cin)
-            conv2d_bwd(tp, r1, da2, da1, 0)
-            bn_backward(tp, bn1, da1, xin, None, ACT_RELU, gX.slice(0, cin), 1)
+            if bn_dgrad_fused_ok(r1, da2):
+                conv2d_bwd(tp, r1, da2, None)
+                bn_dgrad_fused(tp, r1, da2, gX.slice(0, cin), 1)
+            else:
+                da1 = tp.new(B, H, W, cin)
+                conv2d_bwd(tp, r1, da2, da1, 0)
+                bn_backward(tp, bn1, da1, xin, None, ACT_RELU, gX.slice(0, cin), 1)
         tp.on_backward(bwd)
         cin += gr
     return cin
@@ -361,10 +376,15 @@ def transition_body(tp, tr, X, sums, out):
             return
         dtt = tp.new(tt.B, tt.H, tt.W, tt.C)
         _C.call("saunet_avgpool2_bwd", dout.ptr, dout.ld, tt.B, tt.H, tt.W, tt.C, dtt.ptr, dtt.ld, 0, tp.stream)
-        da = tp.new(X.B, X.H, X.W, X.C)
-        conv2d_bwd(tp, r, dtt, da, 0)
-        gX, acc = tp.gw(X)
-        bn_backward(tp, bn, da, X, None, ACT_RELU, gX, acc)
+        if bn_dgrad_fused_ok(r, dtt):
+            conv2d_bwd(tp, r, dtt, None)
+            gX, acc = tp.gw(X)
+            bn_dgrad_fused(tp, r, dtt, gX, acc)      # mean terms settled per slice by the dense block's backward
+        else:
+            da = tp.new(X.B, X.H, X.W, X.C)
+            conv2d_bwd(tp, r, dtt, da, 0)
+            gX, acc = tp.gw(X)
+            bn_backward(tp, bn, da, X, None, ACT_RELU, gX, acc)
     tp.on_backward(bwd)
     return out
 

@@ -29,10 +29,11 @@ def _round4(n):
 
 class Store:
     """One NHWC allocation [npix, ld] plus (lazily) its gradient twin."""
-    __slots__ = ("t", "g", "ld", "npix")
+    __slots__ = ("t", "g", "ld", "npix", "ab")
 
     def __init__(self, t, npix, ld):
         self.t, self.g, self.ld, self.npix = t, None, ld, npix
+        self.ab = 0          # device pointer of double[2][ld]: pending BatchNorm-backward mean terms (see bn_dgrad_fused)
 
 
 class Buf:
@@ -276,7 +277,7 @@ def get_precision():
     return _PRECISION
 
 
-def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None, cm=False):
+def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None, cm=False, wide=False):
     """Tensor-core tiling of a packed [K][N] weight (see saunet_pack_weights_tc) -> (ptr, BN, passes) or None.
     M (GEMM rows) lets small problems take a narrower N tile so that at least ~one CTA per SM exists."""
     if _PRECISION == "fp32":
@@ -284,7 +285,9 @@ def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None, cm=False):
     passes = 3 if _PRECISION == "3xtf32" else 1
     lib = _C.load()
     bn = lib.saunet_tc_tile_n(N)
-    if M is not None:
+    if wide:
+        bn = 128
+    elif M is not None:
         mt = (M + 127) // 128
         # persistent kernels: a 128-wide tile runs at ~2x the efficiency of the narrow ones (MMA operand traffic vs
         # math balance at N = 128), so keep it as long as most SMs get a tile; only really small problems trade tile
@@ -320,7 +323,7 @@ def _p(t):
 # ---------------------------------------------------------------------------
 # thin op wrappers
 def conv(tp, x, wptr, Cout, KH, KW, y, Hg, Wg, sy=1, sx=1, offy=0, offx=0, osy=1, osx=1, oy0=0, ox0=0,
-         pro=0, pro_relu=0, bias=0, row_scale=0, row_add=0.0, act=ACT_NONE, acc=0, stat=None, wtc=None):
+         pro=0, pro_relu=0, bias=0, row_scale=0, row_add=0.0, act=ACT_NONE, acc=0, stat=None, wtc=None, epi=None):
     d = ConvDesc()
     d.x, d.x_ld, d.B, d.Hin, d.Win, d.Cin = x.ptr, x.ld, x.B, x.H, x.W, x.C
     d.w, d.Cout, d.KH, d.KW = wptr, Cout, KH, KW
@@ -342,10 +345,17 @@ def conv(tp, x, wptr, Cout, KH, KW, y, Hg, Wg, sy=1, sx=1, offy=0, offx=0, osy=1
         d.tc_cm = wtc[3] if len(wtc) > 3 else 0
     else:
         d.w_tc, d.tc_bn, d.tc_passes, d.tc_cm = None, 0, 0, 0
+    if epi is not None:        # (xbuf, bn_state_ptr, relu): fused BatchNorm-backward epilogue, see bn_dgrad_fused
+        xb, st, relu = epi
+        d.epi_x, d.epi_x_ld, d.epi_relu = xb.ptr, xb.ld, relu
+        d.epi_scale, d.epi_shift, d.epi_mean = st, st + 4 * xb.C, st + 8 * xb.C
+    else:
+        d.epi_x, d.epi_x_ld, d.epi_scale, d.epi_shift, d.epi_mean, d.epi_relu = None, 0, None, None, None, 0
     M = x.B * Hg * Wg
     _C.call("saunet_conv2d_fwd", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * x.C * Cout,
             nbytes=4.0 * (x.npix * x.C + M * Cout + KH * KW * x.C * Cout),
-            tag="M%d K%dx%dx%d N%d s%d%s%s" % (M, KH, KW, x.C, Cout, sy, " pro" if pro else "", " tc" if wtc else ""))
+            tag="M%d K%dx%dx%d N%d s%d%s%s%s" % (M, KH, KW, x.C, Cout, sy, " pro" if pro else "", " tc" if wtc else "",
+                                                   " bnbwd" if epi is not None else ""))
 
 
 def wgrad(tp, p, q, dwptr, KH, KW, Hg, Wg, sy=1, sx=1, offy=0, offx=0, pro=0, pro_relu=0):
@@ -493,6 +503,49 @@ def conv2d_bwd(tp, r, dy, dx=None, dx_acc=0, need_bias=True):
         conv(tp, dy, packed(tp, w, 1), Cin, KH, KW, dx, x.H, x.W, offy=-(KH - 1 - r.pad), offx=-(KW - 1 - r.pad),
              acc=dx_acc, wtc=packed_tc(tp, w, 1, KH * KW, Cout, Cin, M=x.npix,
                                        cm=_wants_cm(dy, KH, KW, 1, r.pad)) if _tc_ok(dy, Cin, Kd) else None)
+
+
+# ---- 1x1 data gradient fused with the backward of the BatchNorm(+ReLU) in front of the conv ------------------------
+BN_FUSED = os.environ.get("SAUNET_BN_FUSED", "1") == "1"
+
+
+def bn_dgrad_fused_ok(r, dy):
+    """Can conv `r` (a 1x1 / stride-1 conv whose input is relu?(bn(x)) applied as a prologue) take the fused path?"""
+    w = r.w
+    return (BN_FUSED and r.pro is not None and r.k == (1, 1) and r.stride == 1 and r.pad == 0
+            and _tc_ok(dy, w.shape[1], w.shape[0]) and r.x.C % 4 == 0)
+
+
+def bn_dgrad_fused(tp, r, dy, gx, gx_acc):
+    """d loss / d x for  y = conv1x1(relu?(bn(x)))  WITHOUT materialising d loss / d bn-output:
+
+        gx (+)= scale * g,   g = (W^T dy) * relu-mask          -- epilogue of the data-gradient GEMM (conv_pw_t.cu)
+        sums  = [sum g, sum g (x - mean)]                       -- same epilogue
+        dgamma, dbeta, and the mean terms  ab[0][c] + ab[1][c] * x  still owed to gx  -- saunet_bn_fused_finish
+
+    The owed terms accumulate per channel in ``gx.s.ab`` (one double[2][ld] per Store) and are subtracted by
+    ``bn_fixup`` right before a channel range of gx is consumed.  In a DenseNet block every layer's norm1 reads ALL
+    earlier channels: instead of a reduce pass (2 tensors) + an apply pass (4 tensors) over `cin` channels per layer on
+    top of the GEMM's own output, the layer costs one read of x and one read-modify-write of gx inside the GEMM."""
+    bn, x, w = r.pro, r.x, r.w
+    Cout, Cin = w.shape[0], w.shape[1]
+    sums = tp.dzeros(2 * Cin)
+    conv(tp, dy, packed(tp, w, 1), Cin, 1, 1, gx, x.H, x.W, acc=gx_acc, stat=(sums, sums + 8 * Cin),
+         wtc=packed_tc(tp, w, 1, 1, Cout, Cin, wide=True), epi=(x, bn.state, r.pro_relu))
+    if bn.training and not gx.s.ab:
+        gx.s.ab = tp.dzeros(2 * gx.s.ld)
+    mod = bn.mod
+    aff = mod.weight is not None
+    _C.call("saunet_bn_fused_finish", sums, bn.state, float(bn.count), 1 if bn.training else 0, Cin,
+            tp.pgrad(mod.weight) if aff else None, tp.pgrad(mod.bias) if aff else None,
+            (gx.s.ab + 8 * gx.c0) if bn.training else None, gx.s.ld, tp.stream)
+
+
+def bn_fixup(tp, g, x):
+    """Subtract the BatchNorm mean terms still owed to the gradient slice ``g`` (of the activation slice ``x``)."""
+    if g.s.ab:
+        _C.call("saunet_bn_fixup", g.ptr, g.ld, x.ptr, x.ld, g.s.ab + 8 * g.c0, g.s.ld, g.C, g.npix, tp.stream,
+                nbytes=12.0 * g.C * g.npix, tag="C%d npix%d" % (g.C, g.npix))
 
 
 # ---- ConvTranspose2d k4 s2 p1 (attention_blocks.py:179-183, models.py:211) as 4 output phases ----------
