@@ -220,6 +220,16 @@ int saunet_dual_loss_bwd(const float* logits, int l_ld, const float* edge, const
                          long long npix, int C, const float* class_w, const double* acc, const float* dloss,
                          float* dlogits, int dl_ld, float* dedge, int parts, void* stream);
 
+/* ---- optimizer: radam.py:15-78 (RAdam), torch.optim.SGD / Adam as built by train.py:188-207 over the two groups of
+ *      train.py:166-185 -- one fused pass over the flat parameter arena instead of a Python loop over ~700 tensors.
+ * w, g, m, v: flat fp32 arrays of n elements (n % 4 == 0; every tensor starts at a multiple of 4);
+ * seg_table: device array of nseg {long long begin; float lr; float weight_decay} sorted by begin (one per tensor);
+ * step_counter: device int, number of steps taken so far (read, then incremented on the stream): bias corrections and
+ * the RAdam rectification term are computed from it in the kernel, so the call is CUDA-graph capturable.
+ * kind 0 = SGD(momentum, nesterov=False), 1 = Adam, 2 = RAdam (weight decay applied as radam.py:67-68). */
+int saunet_optimizer_step(int kind, float* w, const float* g, float* m, float* v, long long n, const void* seg_table,
+                          int nseg, int* step_counter, float beta1, float beta2, float eps, float momentum, void* stream);
+
 /* ---- Canny fusion: models/models.py:358-364 (np.mean(axis=1).astype(uint8) + cv2.Canny(im,10,100)) ----
  * x is the fp32 image, NCHW [B][C][H][W]; out is float [B][H][W] in {0,255}.
  * workspace: saunet_canny_workspace_bytes(B,H,W) bytes. */

@@ -14,17 +14,22 @@ from . import engine
 
 
 class GraphedStep:
-    def __init__(self, seg_module, arena, example_feed, epoch=0, warmup=2):
+    def __init__(self, seg_module, arena, example_feed, epoch=0, warmup=2, optimizer=None):
         """seg_module: models.SegmentationModule on a CUDA device; arena: parallel.GradArena of its unet;
-        example_feed: dict(image, seg, edge) device tensors with the shapes of every later step."""
-        self.seg_module, self.arena = seg_module, arena
+        example_feed: dict(image, seg, edge) device tensors with the shapes of every later step;
+        optimizer: a saunet_b200.optim.FusedOptimizer to make the weight update part of the captured step (its step
+        counter and hyper-parameter table live on the device; learning-rate changes reach the graph through that
+        table).  The warm-up steps run forward + backward only, so they do not move the weights."""
+        self.seg_module, self.arena, self.optimizer = seg_module, arena, optimizer
         self.static = {k: v.clone() for k, v in example_feed.items()}
         dev = self.static["image"].device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                     # warm-up on the side stream (lazy inits, allocator pools)
             for _ in range(warmup):
-                self._eager(epoch)
+                self._eager(epoch, False)
+        if optimizer is not None:
+            optimizer._segments()                          # build the device table outside the capture (pageable H2D copy)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
@@ -36,15 +41,19 @@ class GraphedStep:
             engine.FORCE_PACK = False
             engine.reset_capture_flags()
 
-    def _eager(self, epoch):
+    def _eager(self, epoch, with_optimizer=True):
         s = self.static
         self.arena.zero()
         loss, acc = self.seg_module({"image": s["image"], "mask": (s["seg"], s["edge"])}, epoch)
         loss.backward()
+        if self.optimizer is not None and with_optimizer:
+            self.optimizer.step()
         return loss.detach(), acc
 
     def __call__(self, feed):
         """feed tensors may live on the host (pinned) or the device; returns the (static) loss tensor."""
+        if self.optimizer is not None:
+            self.optimizer._segments()                     # refresh lr / weight decay in place if a param_group changed
         for k, v in feed.items():
             self.static[k].copy_(v, non_blocking=True)
         self.graph.replay()

@@ -65,6 +65,24 @@ class GradArena:
         self.buckets = [self.flat[i:i + n] for i in range(0, self.n_grad, n)]
         module._saunet_grad_arena = self
 
+    def flatten_params(self):
+        """Move every parameter of the arena into ONE flat fp32 buffer laid out like the gradient arena (same
+        offsets), re-pointing ``p.data`` at views of it: ``nn.Parameter`` identities, shapes and state_dict keys are
+        unchanged (load_state_dict copies into the views).  What the fused optimizer (saunet_b200.optim) steps over."""
+        if getattr(self, "params_flat", None) is not None:
+            return self.params_flat
+        flat = torch.zeros(self.n_grad, dtype=torch.float32, device=self.flat.device)
+        with torch.no_grad():
+            for p in self.params:
+                o = self.offsets[id(p)]
+                v = flat[o:o + p.numel()].view_as(p)
+                v.copy_(p.data)
+                p.data = v
+        self.params_flat = flat
+        from . import engine
+        engine.invalidate_packed()          # data pointers moved: every cached packed image is keyed on them
+        return flat
+
     def ptr(self, p):
         o = self.offsets.get(id(p))
         return None if o is None else self.flat.data_ptr() + 4 * o

@@ -233,6 +233,28 @@ def main():
             print("noise eps", eps, "max norm err", nrm.max(), "max l2", max(l2.values()), max(l2, key=l2.get))
         np.savez_compressed(os.path.join(HERE, "saunet_train_b16_s256_noise.npz"), **out)
         model.load_state_dict(weights)
+    # ---- optimizer golden: the REAL radam.RAdam (radam.py:15-78) on two tensors (a decayed conv weight, an un-decayed
+    # bias), 12 steps (N_sma crosses 5 at step 6: both update branches), seeded gradients
+    if want("optim_radam"):
+        import warnings as _w
+        from radam import RAdam
+        gen = torch.Generator().manual_seed(77)
+        w0 = torch.randn(8, 4, 3, 3, generator=gen)
+        b0 = torch.randn(8, generator=gen)
+        grads = [(torch.randn(8, 4, 3, 3, generator=gen), torch.randn(8, generator=gen)) for _ in range(12)]
+        pw, pb = torch.nn.Parameter(w0.clone()), torch.nn.Parameter(b0.clone())
+        with _w.catch_warnings():
+            _w.simplefilter("ignore")
+            opt = RAdam([dict(params=[pw], weight_decay=1e-2), dict(params=[pb], weight_decay=0.0)], lr=1e-2)
+            ws, bs = [], []
+            for gw, gb in grads:
+                pw.grad, pb.grad = gw.clone(), gb.clone()
+                opt.step()
+                ws.append(np32(pw)); bs.append(np32(pb))
+        np.savez_compressed(os.path.join(HERE, "optim_radam.npz"), w0=np32(w0), b0=np32(b0),
+                            gw=np.stack([np32(g[0]) for g in grads]), gb=np.stack([np32(g[1]) for g in grads]),
+                            w=np.stack(ws), b=np.stack(bs), lr=np.float64(1e-2), wd=np.float64(1e-2))
+        print("optim_radam: |w12 - w0| =", float((pw.detach() - w0).abs().max()))
     if only and not (only & {"blocks", "loss", "canny"}):
         return
 

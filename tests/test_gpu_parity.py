@@ -486,6 +486,111 @@ def test_weight_updates_through_data_are_seen():
     assert abs(lg2 - lg) < 1e-5 * abs(lg)
 
 
+def _tiny_net():
+    return torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Conv2d(8, 6, 1, bias=False))
+
+
+@pytest.mark.parametrize("kind", ["sgd", "adam", "radam"])
+def test_fused_optimizer_matches_reference(kind):
+    """saunet_b200.optim.FusedOptimizer (ONE launch over the flat parameter arena) against the reference optimizers on
+    the same gradients for 12 steps: torch.optim.SGD(momentum, weight decay groups of train.py:166-185) / torch.optim.Adam
+    on the CPU, and for RAdam the oracle restatement of radam.py:15-78 (pinned to the real radam.RAdam by
+    tests/golden/optim_radam.npz, which is also replayed here)."""
+    from saunet_b200.optim import FusedOptimizer, create_fused_optimizer, group_weight
+    from saunet_b200.parallel import GradArena
+    from oracle import optim_oracle as OO
+    torch.manual_seed(3)
+    net = _tiny_net().to(DEV)
+    ref = _tiny_net()
+    ref.load_state_dict(net.state_dict())
+    arena = GradArena(net)
+    opt = create_fused_optimizer(net, arena, kind, lr=1e-2, momentum=0.9, weight_decay=1e-2)
+    keys = [k for k, _ in net.named_parameters()]
+    assert [k for k, _ in ref.named_parameters()] == keys
+    if kind == "sgd":
+        ropt = torch.optim.SGD(group_weight(ref), lr=1e-2, momentum=0.9, weight_decay=1e-2, nesterov=False)
+    elif kind == "adam":
+        ropt = torch.optim.Adam(group_weight(ref), lr=1e-2, betas=(0.9, 0.999))
+    else:
+        ropt = None
+        rstate = {k: [np.zeros(p.shape, np.float32), np.zeros(p.shape, np.float32)] for k, p in ref.named_parameters()}
+        rw = {k: p.detach().numpy().copy() for k, p in ref.named_parameters()}
+    gen = torch.Generator().manual_seed(5)
+    for t in range(12):
+        if t == 6:                                   # adjust_learning_rate (train.py:210-216) mid-run
+            for g in opt.param_groups:
+                g["lr"] = 5e-3
+            if ropt is not None:
+                for g in ropt.param_groups:
+                    g["lr"] = 5e-3
+        lr = 1e-2 if t < 6 else 5e-3
+        opt.zero_grad()
+        for (k, p), pr in zip(net.named_parameters(), ref.parameters()):
+            gr = torch.randn(p.shape, generator=gen)
+            p.grad.copy_(gr.to(DEV))
+            assert p.grad.data_ptr() == arena.ptr(p)
+            if ropt is not None:
+                pr.grad = gr.clone()
+            else:
+                OO.radam_step(rw[k], gr.numpy(), rstate[k][0], rstate[k][1], t, lr)     # create_optimizers: RAdam has no weight decay
+        opt.step()
+        if ropt is not None:
+            ropt.step()
+        for (k, p), pr in zip(net.named_parameters(), ref.parameters()):
+            want = pr.detach() if ropt is not None else torch.from_numpy(rw[k])
+            assert float((p.detach().cpu() - want).abs().max()) < 2e-6 * max(1.0, float(want.abs().max())), (kind, t, k)
+    assert int(opt.step_counter) == 12
+    if kind == "radam":     # the real radam.RAdam fixture: weight decay 1e-2 on the conv weight, none on the bias
+        g = load_golden("optim_radam")
+        m = torch.nn.Conv2d(4, 8, 3).to(DEV)
+        with torch.no_grad():
+            m.weight.copy_(torch.from_numpy(g["w0"])); m.bias.copy_(torch.from_numpy(g["b0"]))
+        a2 = GradArena(m)
+        o2 = FusedOptimizer([dict(params=[m.weight], weight_decay=float(g["wd"])), dict(params=[m.bias], weight_decay=0.0)],
+                            a2, "radam", lr=float(g["lr"]))
+        for t in range(12):
+            m.weight.grad.copy_(torch.from_numpy(g["gw"][t])); m.bias.grad.copy_(torch.from_numpy(g["gb"][t]))
+            o2.step()
+            assert float((m.weight.detach().cpu() - torch.from_numpy(g["w"][t])).abs().max()) < 2e-6, t
+            assert float((m.bias.detach().cpu() - torch.from_numpy(g["b"][t])).abs().max()) < 2e-6, t
+
+
+def test_fused_optimizer_in_training_step_and_graph():
+    """The fused optimizer inside the real step: weights move, the packed-weight images follow (forward changes), and
+    a CUDA-graph capture of fwd + bwd + optimizer step replays to the same losses as the eager loop."""
+    from loss import DualLoss
+    from models import SegmentationModule
+    from saunet_b200.graphs import GraphedStep
+    from saunet_b200.optim import create_fused_optimizer
+    from saunet_b200.parallel import GradArena
+    d = {k: v.to(DEV) for k, v in synth.synthetic_batch(2, 64, seed=304).items()}
+    feed = {"image": d["image"], "mask": (d["seg"], d["edge"])}
+
+    def build():
+        unet = _model(True)
+        seg_mod = SegmentationModule(DualLoss(), unet, 4).to(DEV).train()
+        arena = GradArena(unet)
+        opt = create_fused_optimizer(unet, arena, "radam", lr=1e-3)
+        return unet, seg_mod, arena, opt
+
+    unet, seg_mod, arena, opt = build()
+    sd_keys = list(unet.state_dict().keys())
+    eager = []
+    for _ in range(4):
+        opt.zero_grad()
+        loss, _ = seg_mod(feed, 0)
+        loss.backward()
+        opt.step()
+        eager.append(float(loss))
+    assert len(set(eager)) == 4 and list(unet.state_dict().keys()) == sd_keys
+    unet2, seg_mod2, arena2, opt2 = build()
+    g = GraphedStep(seg_mod2, arena2, d, optimizer=opt2)
+    graphed = [float(g(d)) for _ in range(4)]
+    # (fp32 atomics order differs between runs; four RAdam steps at lr 1e-3 keep the two trajectories together)
+    for a, b in zip(eager, graphed):
+        assert abs(a - b) < 2e-4 * abs(a), (eager, graphed)
+
+
 def test_loss_ignores_out_of_range_labels():
     """labels outside [0,C) (255 = unlabeled, -100 = CrossEntropyLoss's ignore_index) must never be used
     as an index: they contribute to no sum and are counted."""

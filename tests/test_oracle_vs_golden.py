@@ -92,6 +92,21 @@ def test_b16_fixture_is_the_headline_config():
     assert 0.0 <= float(acc) <= 1.0
 
 
+def test_radam_oracle_matches_reference():
+    """oracle/optim_oracle.py (radam.py:15-78 restated) against 12 steps of the real radam.RAdam."""
+    from oracle import optim_oracle as OO
+    g = load_golden("optim_radam")
+    w, b = g["w0"].copy(), g["b0"].copy()
+    st = [np.zeros_like(w), np.zeros_like(w), np.zeros_like(b), np.zeros_like(b)]
+    crossed = False
+    for t in range(12):
+        n = OO.radam_step(w, g["gw"][t], st[0], st[1], t, float(g["lr"]), weight_decay=float(g["wd"]))
+        OO.radam_step(b, g["gb"][t], st[2], st[3], t, float(g["lr"]))
+        crossed |= n >= 5
+        assert np.abs(w - g["w"][t]).max() < 2e-6 and np.abs(b - g["b"][t]).max() < 2e-6, t
+    assert crossed
+
+
 def test_loss_matches_reference():
     g = load_golden("loss_dual")
     seg = torch.from_numpy(g["seg"]).requires_grad_(True)
