@@ -230,6 +230,14 @@ int saunet_dual_loss_bwd(const float* logits, int l_ld, const float* edge, const
 int saunet_optimizer_step(int kind, float* w, const float* g, float* m, float* v, long long n, const void* seg_table,
                           int nseg, int* step_counter, float beta1, float beta2, float eps, float momentum, void* stream);
 
+/* ---- volume inference (test_and_pack.py:98-137) and loader-side data prep (data/ac17_dataloader.py:231-258) ----
+ * argmax over the C logits of every pixel (first maximum on ties, as torch.max) -> uint8 label map */
+int saunet_argmax_u8(const float* logits, int ld, int C, long long npix, unsigned char* out, void* stream);
+/* edge ground truth of a label map (int64 [B][H][W], classes 1..num_classes): out[p] = 1.0 iff a pixel within Euclidean
+ * distance `radius` (2 in the reference) carries a different label, pixels just outside the image counting as 0 --
+ * identical to the reference's two-distance-transforms-per-class construction (mask_to_edges) */
+int saunet_edge_gt(const long long* seg, int B, int H, int W, int radius, int num_classes, float* out, void* stream);
+
 /* ---- Canny fusion: models/models.py:358-364 (np.mean(axis=1).astype(uint8) + cv2.Canny(im,10,100)) ----
  * x is the fp32 image, NCHW [B][C][H][W]; out is float [B][H][W] in {0,255}.
  * workspace: saunet_canny_workspace_bytes(B,H,W) bytes. */

@@ -77,6 +77,8 @@ SIGNATURES = {
     "saunet_dual_loss_fwd": [_P, _I, _P, _P, _P, _L, _I, _P, _I, _P, _P, _P, _P],
     "saunet_dual_loss_bwd": [_P, _I, _P, _P, _P, _L, _I, _P, _P, _P, _P, _I, _P, _I, _P],
     "saunet_optimizer_step": [_I, _P, _P, _P, _P, _L, _P, _I, _P, _F, _F, _F, _F, _P],
+    "saunet_argmax_u8": [_P, _I, _I, _L, _P, _P],
+    "saunet_edge_gt": [_P, _I, _I, _I, _I, _I, _P, _P],
     "saunet_canny_fwd": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],
 }
 _SPECIAL = {

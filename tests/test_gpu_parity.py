@@ -591,6 +591,52 @@ def test_fused_optimizer_in_training_step_and_graph():
         assert abs(a - b) < 2e-4 * abs(a), (eager, graphed)
 
 
+def test_edge_gt_matches_loader_construction():
+    """saunet_edge_gt (a radius-2 label-difference stencil) == the loader's construction (data/ac17_dataloader.py:231-258:
+    two Euclidean distance transforms per class on the 1-padded one-hot map), restated with scipy in synth.mask_to_edges
+    -- bit-exact, including shapes that touch the image border and labels outside 1..3."""
+    from saunet_b200.inference import edge_ground_truth
+    rng = np.random.default_rng(5)
+    segs = [synth.synthetic_batch(3, 96, seed=9)["seg"]]
+    blob = torch.zeros(4, 40, 56, dtype=torch.int64)
+    blob[0, :7, :9] = 1; blob[0, 30:, 50:] = 2; blob[0, 10:12, 20:22] = 3          # corners, thin shapes
+    blob[1] = torch.from_numpy(rng.integers(0, 4, (40, 56)))                         # salt and pepper
+    blob[2, 5:35, 5:50] = 3; blob[2, 15:25, 15:40] = 2; blob[2, 19:21, 0:3] = 1      # nested + border-touching
+    blob[3, :, 0] = 1; blob[3, 0, :] = 2; blob[3, 20, 20] = 7                        # edges of the image; a label out of range
+    segs.append(blob)
+    for seg in segs:
+        got = edge_ground_truth(seg.to(DEV)).cpu().numpy()
+        want = np.stack([synth.mask_to_edges(seg[b].numpy()) for b in range(seg.shape[0])]).astype(np.float32)
+        assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_volume_inference_vs_oracle():
+    """BASELINE configs[4]: a 16-slice 256x256 stack as ONE batch in eval mode, argmax on the device, against the CPU
+    oracle's per-slice argmax: Dice per class and voxel agreement (argmax can flip where two logits tie to ~1e-5)."""
+    from oracle import saunet_oracle as O
+    from saunet_b200.inference import argmax_u8, dice_per_class, predict_volume
+    torch.set_num_threads(max(8, torch.get_num_threads()))
+    data = synth.synthetic_batch(16, 256, seed=21)
+    w = synth.synthetic_state_dict(template_state_dict(), seed=0)
+    with torch.no_grad():
+        ref_logits, _ = O.saunet_forward(O.prepare_params(w), data["image"], training=False)
+    ref = ref_logits.argmax(dim=1).to(torch.uint8)
+    m = _model(False)
+    vol = predict_volume(m, data["image"].to(DEV))
+    assert vol.shape == (16, 256, 256) and vol.dtype == torch.uint8
+    agree = float((vol.cpu() == ref).float().mean())
+    dice = dice_per_class(vol.cpu(), ref)
+    assert agree > 0.9995, agree
+    assert all(d > 0.999 for d in dice), dice
+    # the reference's loader layout [C,H,W,Z] (test_and_pack.py:105-109) gives the same volume
+    vol2 = predict_volume(m, data["image"].permute(1, 2, 3, 0).contiguous().to(DEV))
+    assert float((vol2 == vol).float().mean()) > 0.9999      # (atomics in the SE pooling: near-ties may flip)
+    z = torch.randn(2, 5, 7, 9, device=DEV)
+    assert torch.equal(argmax_u8(z.contiguous(memory_format=torch.channels_last)).long(), z.argmax(dim=1))
+    with pytest.raises(RuntimeError):
+        predict_volume(_model(True), data["image"][:1].to(DEV))
+
+
 def test_loss_ignores_out_of_range_labels():
     """labels outside [0,C) (255 = unlabeled, -100 = CrossEntropyLoss's ignore_index) must never be used
     as an index: they contribute to no sum and are counted."""
