@@ -21,6 +21,7 @@ from . import _C
 from ._C import ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, WgradDesc
 
 BN_EPS = 1e-5
+OVERLAP = os.environ.get("SAUNET_OVERLAP", "1") == "1"      # post-process gradient buckets on a side stream during backward
 
 
 def _round4(n):
@@ -88,6 +89,7 @@ class Tape:
         self.bn_tracked = []
         self.arena = None
         self.used_packed = False
+        self._touch, self._cur = None, 0
         self.repacked = []      # pack-cache entries refreshed under FORCE_PACK by this tape (flag reset at the end)
 
     # ---- memory ---------------------------------------------------------
@@ -156,6 +158,8 @@ class Tape:
         if self.arena is not None:
             ptr = self.arena.ptr(p)
             if ptr is not None:
+                if self._touch is not None:
+                    self._touch[id(p)] = self._cur
                 return ptr
         g = self.pgrads.get(p)
         if g is None:
@@ -170,16 +174,36 @@ class Tape:
             ptr = self.arena.packed_ptr(p)
             if ptr is not None:
                 self.used_packed = True
+                if self._touch is not None:
+                    self._touch[id(p)] = self._cur
                 return ptr
         return None
 
     def backward(self):
-        for fn in reversed(self.ops):
+        """Replay the tape in reverse.  With a GradArena attached, the arena's buckets are post-processed (packed
+        conv-weight gradients folded, gradients all-reduced when N > 1) on a side stream as soon as the LAST op that
+        writes into them has run, overlapping the rest of backward; the op index per bucket is learnt from the first
+        backward of a tape of this length (the op sequence of a model is static)."""
+        arena = self.arena
+        n = len(self.ops)
+        sched = arena.schedule_for(n) if (arena is not None and OVERLAP) else None
+        self._touch = {} if (arena is not None and sched is None) else None
+        for i, fn in enumerate(reversed(self.ops)):
+            self._cur = i
             fn()
+            if sched is not None and i in sched:
+                for b in sched[i]:
+                    arena.bucket_ready(b)
         self.ops = []
-        if self.used_packed:
-            self.arena.unpack(self.stream)
-            self.used_packed = False
+        if arena is not None:
+            if sched is None:
+                if self.used_packed:
+                    arena.unpack(self.stream)
+                if self._touch is not None and n:
+                    arena.learn_schedule(n, self._touch)
+            elif not arena._works:
+                arena.join()                       # nothing left in flight but the unpack kernels: join now
+        self.used_packed = False
 
     def on_backward(self, fn):
         if self.record:

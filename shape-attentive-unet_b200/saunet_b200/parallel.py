@@ -61,9 +61,97 @@ class GradArena:
             o = self.offsets[id(p)]
             self._views[id(p)] = self.flat[o:o + p.numel()].view_as(p)
             p.grad = self._views[id(p)]
+        # Buckets = contiguous parameter ranges of ~bucket_mb each.  Parameters are laid out in forward (module) order, so
+        # backward completes them from the END of the arena: the last bucket is final first.  Each bucket carries the
+        # unpack table of its own conv weights, so that "fold the packed weight gradients + all-reduce" can be issued
+        # per bucket on a side stream while the rest of backward still runs (see bucket_ready / Tape.backward).
         n = max(1, int(bucket_mb * (1 << 20) // 4))
-        self.buckets = [self.flat[i:i + n] for i in range(0, self.n_grad, n)]
+        self.bucket_params, cur, start = [], [], 0
+        for p in params:
+            cur.append(p)
+            end = self.offsets[id(p)] + (p.numel() + 3) // 4 * 4
+            if end - start >= n:
+                self.bucket_params.append((start, end, cur))
+                cur, start = [], end
+        if cur:
+            self.bucket_params.append((start, self.n_grad, cur))
+        self.buckets = [self.flat[a:b] for a, b, _ in self.bucket_params]
+        self._bucket_of = {id(p): i for i, (_, _, ps) in enumerate(self.bucket_params) for p in ps}
+        self._bucket_tables = []
+        for _, _, ps in self.bucket_params:
+            ents, first = [], 0
+            for p in ps:
+                if p.dim() == 4:
+                    a_, b_, kh, kw = p.shape
+                    ents.append((first, self.packed_off[id(p)] - self.n_grad, self.offsets[id(p)], a_, b_, kh * kw))
+                    first += p.numel()
+            self._bucket_tables.append((self._make_table(ents, dev) if ents else None, len(ents), first))
+        self._schedule = None          # (n_ops, {op index -> [bucket, ...]}) learnt from the first backward
+        self._comm = None              # side stream for unpack + all-reduce
+        self._works = []
+        self._overlapped = False
         module._saunet_grad_arena = self
+
+    @staticmethod
+    def _make_table(entries, dev):
+        from . import _C
+        arr = (_C.UnpackEntry * len(entries))()
+        for i, e in enumerate(entries):
+            arr[i].first, arr[i].packed_off, arr[i].grad_off, arr[i].A, arr[i].Bc, arr[i].T = e
+        return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+
+    # ---- overlap of gradient post-processing with backward -----------------------------------------------------
+    def learn_schedule(self, n_ops, last_touch):
+        """last_touch: {id(param): index (in execution order) of the last backward op that wrote its gradient}.
+        A bucket is final after the latest such op among its parameters (-1: never written, e.g. unused heads)."""
+        sched = {}
+        for b, (_, _, ps) in enumerate(self.bucket_params):
+            k = max([last_touch.get(id(p), -1) for p in ps] + [-1])
+            sched.setdefault(max(k, 0), []).append(b)
+        self._schedule = (n_ops, sched)
+
+    def schedule_for(self, n_ops):
+        return self._schedule[1] if self._schedule is not None and self._schedule[0] == n_ops else None
+
+    def _world(self, group=None):
+        return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+
+    def bucket_ready(self, b):
+        """Called from Tape.backward right after the op that finalises bucket ``b``: on the side stream, fold the bucket's
+        packed conv-weight gradients into parameter layout and (N > 1, not under graph capture) start its all-reduce --
+        both overlap the remaining backward kernels."""
+        dev = self.flat.device
+        cur = torch.cuda.current_stream(dev)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._comm.wait_event(ev)
+        capturing = torch.cuda.is_current_stream_capturing()
+        with torch.cuda.stream(self._comm):
+            tab, n, total = self._bucket_tables[b]
+            if n:
+                from . import _C
+                _C.call("saunet_unpack_wgrad_multi", tab.data_ptr(), n, total, self.packed.data_ptr(), self.flat.data_ptr(),
+                        self._comm.cuda_stream)
+            world = self._world()
+            if world > 1 and not capturing:
+                op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+                self._works.append((dist.all_reduce(self.buckets[b], op=op, async_op=True), b, op))
+        self._overlapped = True
+
+    def join(self):
+        """Make the current stream wait for everything issued by bucket_ready (end of backward / before the optimizer)."""
+        if self._comm is None:
+            return
+        dev = self.flat.device
+        world = self._world()
+        with torch.cuda.stream(self._comm):
+            for w, b, op in self._works:
+                w.wait()
+                if op == dist.ReduceOp.SUM:
+                    self.buckets[b].mul_(1.0 / world)
+        torch.cuda.current_stream(dev).wait_stream(self._comm)
 
     def flatten_params(self):
         """Move every parameter of the arena into ONE flat fp32 buffer laid out like the gradient arena (same
@@ -120,16 +208,26 @@ class GradArena:
             self.attach()
 
     def all_reduce(self, group=None):
-        """SUM-reduce in place and scale by 1/world (mean over ranks)."""
+        """Mean of the gradients over ranks, in place.  When the backward that just ran overlapped its buckets
+        (bucket_ready), the all-reduces are already in flight: only wait for them."""
         if not (dist.is_available() and dist.is_initialized()):
+            self._works = []
             return
         world = dist.get_world_size(group)
         if world == 1:
+            self._works = []
             return
-        works = [dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group, async_op=True) for b in self.buckets]
+        if self._works:
+            self.join()
+            self._works = []
+            return
+        nccl = dist.get_backend(group) == "nccl"
+        op = dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM
+        works = [dist.all_reduce(b, op=op, group=group, async_op=True) for b in reversed(self.buckets)]
         for w in works:
             w.wait()
-        self.flat.mul_(1.0 / world)
+        if not nccl:
+            self.flat.mul_(1.0 / world)
 
 
 def shard_batch(n_items, rank, world):
