@@ -229,7 +229,7 @@ def dice_loss(true, logits, eps=1e-7):
 
 def dual_loss(seg, edge_in, seg_t, edge_t, parts=False):
     """loss.py:149-159 (DualLoss.forward): dice + weighted CE + edge BCE."""
-    w = torch.tensor(CE_WEIGHTS, dtype=seg.dtype)[: seg.shape[1]]
+    w = torch.tensor(CE_WEIGHTS, dtype=seg.dtype, device=seg.device)[: seg.shape[1]]
     ce = F.cross_entropy(seg, seg_t.long(), weight=w)
     dice = dice_loss(seg_t, seg)
     bce = F.binary_cross_entropy(edge_in, edge_t.to(edge_in.dtype))

@@ -132,6 +132,7 @@ def check(rc, name="saunet"):
 # When set to a list, every call is bracketed by CUDA events on the current stream and appended as
 # (name, start_event, end_event, flops, bytes): bench.py's per-kernel roofline pass.  None on the normal path.
 PROFILE = None
+SCOPE = ""         # bench.py --workload blocks: label (e.g. "tail") prefixed to the tag of every call made while it is set
 
 
 def call(name, *args, flops=0, nbytes=0, tag=""):
@@ -142,7 +143,7 @@ def call(name, *args, flops=0, nbytes=0, tag=""):
         rc = getattr(load(), name)(*args)
         e1.record()
         kern = load().saunet_last_kernel()
-        PROFILE.append((name, e0, e1, flops, nbytes, tag, kern.decode() if kern else name))
+        PROFILE.append((name, e0, e1, flops, nbytes, (SCOPE + ":" + tag) if SCOPE else tag, kern.decode() if kern else name))
     else:
         rc = getattr(load(), name)(*args)
     if rc != 0:

@@ -201,7 +201,7 @@ class Tape:
                     arena.unpack(self.stream)
                 if self._touch is not None and n:
                     arena.learn_schedule(n, self._touch)
-            elif not arena._works:
+            elif not arena._works or torch.cuda.is_current_stream_capturing():
                 arena.join()                       # nothing left in flight but the unpack kernels: join now
         self.used_packed = False
 

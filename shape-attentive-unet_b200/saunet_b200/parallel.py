@@ -90,6 +90,7 @@ class GradArena:
         self._comm = None              # side stream for unpack + all-reduce
         self._works = []
         self._overlapped = False
+        self.comm_enabled = True       # False (see no_sync): bucket_ready only folds the packed gradients, no collective
         module._saunet_grad_arena = self
 
     @staticmethod
@@ -135,10 +136,24 @@ class GradArena:
                 _C.call("saunet_unpack_wgrad_multi", tab.data_ptr(), n, total, self.packed.data_ptr(), self.flat.data_ptr(),
                         self._comm.cuda_stream)
             world = self._world()
-            if world > 1 and not capturing:
+            if world > 1 and not capturing and self.comm_enabled:
                 op = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
                 self._works.append((dist.all_reduce(self.buckets[b], op=op, async_op=True), b, op))
         self._overlapped = True
+
+    def no_sync(self):
+        """Context manager: backward passes inside it issue NO collective (like DistributedDataParallel.no_sync) -- for
+        gradient accumulation, and for anything only some ranks execute (e.g. a rank-0-only profiling pass: a
+        collective the other ranks never enter would deadlock the job)."""
+        arena = self
+
+        class _NoSync:
+            def __enter__(self_):
+                self_.prev, arena.comm_enabled = arena.comm_enabled, False
+
+            def __exit__(self_, *a):
+                arena.comm_enabled = self_.prev
+        return _NoSync()
 
     def join(self):
         """Make the current stream wait for everything issued by bucket_ready (end of backward / before the optimizer)."""
