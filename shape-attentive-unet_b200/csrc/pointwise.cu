@@ -216,6 +216,41 @@ __global__ void __launch_bounds__(256) gap_fwd_kernel(const float* __restrict__ 
         atomicAdd(y + (size_t)b * C + c, s * inv);
     }
 }
+// C % 4 == 0, 16-byte aligned rows: lane = 4 channels (one 512-byte request per warp and pixel row), 4 rows in flight per
+// thread.  (The scalar kernel above reads 128 bytes per request with one load in flight: 2.2 TB/s at C = 256.)
+__global__ void __launch_bounds__(256) gap_fwd4_kernel(const float* __restrict__ x, int x_ld, long long HW, int C, float* y, float inv) {
+    __shared__ float4 red[8][32];
+    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * 4, b = blockIdx.y;
+    const long long per = (HW + gridDim.z - 1) / gridDim.z;
+    const long long p0 = blockIdx.z * per; long long p1 = p0 + per; if (p1 > HW) p1 = HW;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+        const float* base = x + (size_t)b * HW * x_ld + c;
+        long long p = p0 + r;
+        for (; p + 24 < p1; p += 32) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * x_ld));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(base + (size_t)(p + 8) * x_ld));
+            const float4 a2 = __ldg(reinterpret_cast<const float4*>(base + (size_t)(p + 16) * x_ld));
+            const float4 a3 = __ldg(reinterpret_cast<const float4*>(base + (size_t)(p + 24) * x_ld));
+            acc.x += (a0.x + a1.x) + (a2.x + a3.x); acc.y += (a0.y + a1.y) + (a2.y + a3.y);
+            acc.z += (a0.z + a1.z) + (a2.z + a3.z); acc.w += (a0.w + a1.w) + (a2.w + a3.w);
+        }
+        for (; p < p1; p += 8) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(base + (size_t)p * x_ld));
+            acc.x += a0.x; acc.y += a0.y; acc.z += a0.z; acc.w += a0.w;
+        }
+    }
+    red[r][lane] = acc;
+    __syncthreads();
+    if (r == 0 && c < C) {
+        float4 s = red[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { s.x += red[k][lane].x; s.y += red[k][lane].y; s.z += red[k][lane].z; s.w += red[k][lane].w; }
+        float* yp = y + (size_t)b * C + c;
+        atomicAdd(yp, s.x * inv); atomicAdd(yp + 1, s.y * inv); atomicAdd(yp + 2, s.z * inv); atomicAdd(yp + 3, s.w * inv);
+    }
+}
 template <int VEC>
 __global__ void __launch_bounds__(256) gap_bwd_kernel(const float* __restrict__ dy, int B, long long HW, int C, float* dx, int dx_ld,
                                                       int accumulate, float inv) {
@@ -302,6 +337,82 @@ __global__ void __launch_bounds__(256) dualatt_bwd_kernel(const float* __restric
     for (int k = 0; k < MAXCH; ++k) red[w][k * 32 + lane] = accc[k];
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * MAXCH; i += 256) {
+        if (i < C) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += red[k][i];
+            atomicAdd(dcv + (size_t)b * C + i, s);
+        }
+    }
+}
+
+// C % 4 == 0, 16-byte aligned rows: lane = 4 channels, all loads of a pixel issued before its stores, two pixels in flight
+// per warp.  (The scalar kernel above interleaves 4-byte loads and stores: 0.6 ms = 2.7 TB/s at C = 256, 524288 pixels.)
+template <int K4>
+__global__ void __launch_bounds__(256) dualatt_bwd4_kernel(const float* __restrict__ dout, int do_ld, const float* __restrict__ f, int f_ld,
+                                                           const float* __restrict__ S, const float* __restrict__ cv, long long HW, int C,
+                                                           float* df, int df_ld, int df_acc, float* __restrict__ dS, float* dcv) {
+    __shared__ float red[8][128 * K4 + 4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, b = blockIdx.y;
+    const long long per = (HW + gridDim.x - 1) / gridDim.x;
+    const long long p0 = blockIdx.x * per; long long p1 = p0 + per; if (p1 > HW) p1 = HW;
+    float4 accc[K4], cvr[K4];
+#pragma unroll
+    for (int k = 0; k < K4; ++k) {
+        accc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = (k * 32 + lane) * 4;
+        cvr[k] = c < C ? __ldg(reinterpret_cast<const float4*>(cv + (size_t)b * C + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long pl = p0 + w; pl < p1; pl += 16) {
+        float4 g[2][K4], fv[2][K4], od[2][K4];
+        float s1[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long pp = pl + 8 * u;
+            const long long p = (long long)b * HW + pp;
+            s1[u] = pp < p1 ? __ldg(S + p) + 1.f : 0.f;
+#pragma unroll
+            for (int k = 0; k < K4; ++k) {
+                const int c = (k * 32 + lane) * 4;
+                if (pp < p1 && c < C) {
+                    g[u][k] = __ldg(reinterpret_cast<const float4*>(dout + (size_t)p * do_ld + c));
+                    fv[u][k] = __ldg(reinterpret_cast<const float4*>(f + (size_t)p * f_ld + c));
+                    if (df_acc) od[u][k] = *reinterpret_cast<const float4*>(df + (size_t)p * df_ld + c);
+                } else {
+                    g[u][k] = fv[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const long long pp = pl + 8 * u;
+            if (pp >= p1) continue;                      // warp-uniform
+            const long long p = (long long)b * HW + pp;
+            float accS = 0.f;
+#pragma unroll
+            for (int k = 0; k < K4; ++k) {
+                const int c = (k * 32 + lane) * 4;
+                const float4 t = make_float4(g[u][k].x * fv[u][k].x, g[u][k].y * fv[u][k].y, g[u][k].z * fv[u][k].z, g[u][k].w * fv[u][k].w);
+                accS += t.x * cvr[k].x + t.y * cvr[k].y + t.z * cvr[k].z + t.w * cvr[k].w;
+                accc[k].x = fmaf(t.x, s1[u], accc[k].x); accc[k].y = fmaf(t.y, s1[u], accc[k].y);
+                accc[k].z = fmaf(t.z, s1[u], accc[k].z); accc[k].w = fmaf(t.w, s1[u], accc[k].w);
+                if (c < C) {
+                    float4 d = make_float4(g[u][k].x * s1[u] * cvr[k].x, g[u][k].y * s1[u] * cvr[k].y, g[u][k].z * s1[u] * cvr[k].z, g[u][k].w * s1[u] * cvr[k].w);
+                    if (df_acc) { d.x += od[u][k].x; d.y += od[u][k].y; d.z += od[u][k].z; d.w += od[u][k].w; }
+                    *reinterpret_cast<float4*>(df + (size_t)p * df_ld + c) = d;
+                }
+            }
+            accS = warp_sum(accS);
+            if (lane == 0) dS[p] = accS;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K4; ++k) {
+        float* r = &red[w][(k * 32 + lane) * 4];
+        r[0] = accc[k].x; r[1] = accc[k].y; r[2] = accc[k].z; r[3] = accc[k].w;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 128 * K4; i += 256) {
         if (i < C) {
             float s = 0.f;
 #pragma unroll
@@ -463,6 +574,14 @@ extern "C" int saunet_gap_fwd(const float* x, int x_ld, int B, long long HW, int
     int cb = cdiv(C, 32);
     long long splits = (long long)kNumSMs * 4 / ((long long)cb * B); if (splits < 1) splits = 1;
     long long maxs = (HW + 63) / 64; if (splits > maxs) splits = maxs;
+    if (C % 4 == 0 && x_ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0)) {
+        const int cb4 = (C / 4 + 31) / 32;
+        long long sp = (long long)kNumSMs * 8 / ((long long)cb4 * B); if (sp < 1) sp = 1;
+        long long mx = (HW + 255) / 256; if (sp > mx) sp = mx;
+        gap_fwd4_kernel<<<dim3(cb4, B, (unsigned)sp), 256, 0, ST>>>(x, x_ld, HW, C, y, 1.0f / (float)HW);
+        SAUNET_CHECK_LAUNCH("gap_fwd4_kernel");
+        return SAUNET_OK;
+    }
     gap_fwd_kernel<<<dim3(cb, B, (unsigned)splits), 256, 0, ST>>>(x, x_ld, HW, C, y, 1.0f / (float)HW);
     SAUNET_CHECK_LAUNCH("gap_fwd_kernel");
     return SAUNET_OK;
@@ -497,6 +616,14 @@ extern "C" int saunet_dualatt_combine_bwd(const float* dout, int do_ld, const fl
     long long chunks = (long long)kNumSMs * 4 / B; if (chunks < 1) chunks = 1;
     long long maxc = (HW + 31) / 32; if (chunks > maxc) chunks = maxc;
     dim3 grid((unsigned)chunks, B);
+    if (C % 4 == 0 && C <= 512 && do_ld % 4 == 0 && f_ld % 4 == 0 && df_ld % 4 == 0 && aligned16(dout) && aligned16(fused) && aligned16(dfused) &&
+        aligned16(cvec)) {
+        if (C <= 128) dualatt_bwd4_kernel<1><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
+        else if (C <= 256) dualatt_bwd4_kernel<2><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
+        else dualatt_bwd4_kernel<4><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
+        SAUNET_CHECK_LAUNCH("dualatt_bwd4_kernel");
+        return SAUNET_OK;
+    }
     if (C <= 64) dualatt_bwd_kernel<2><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
     else if (C <= 128) dualatt_bwd_kernel<4><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);
     else if (C <= 256) dualatt_bwd_kernel<8><<<grid, 256, 0, ST>>>(dout, do_ld, fused, f_ld, S, cvec, HW, C, dfused, df_ld, df_acc, dS, dcvec);

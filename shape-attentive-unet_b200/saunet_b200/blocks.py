@@ -125,8 +125,150 @@ def basic_block_body(tp, m, x, out=None):
 
 
 # ---------------------------------------------------------------------------
+# GatedSpatialConv2d with C+1 gate channels padded to a multiple of 4.  The gate's (C+1)->(C+1) convolution is the
+# block's only real arithmetic (2(C+1)^2 FLOP per pixel); with an odd channel count it can only run on the scalar FFMA
+# kernels (257 -> 257 at 128x128, batch 32: 6.5 ms forward, 9.2 ms weight gradient).  Zero channels / zero weight rows and
+# columns change nothing mathematically and put the three gate convolutions on the tensor-core kernels.
+GS_PAD_MIN = 41          # pad when C+1 >= this (smaller gates: the per-pixel skinny kernels are as fast)
+
+
+class _PadBN:
+    """Stands in for a BatchNorm module over the padded channel count (what bn_finalize / bn_backward read)."""
+
+    def __init__(self, real, Cp):
+        dev = real.running_mean.device
+        self.real, self.Cp, self.C = real, Cp, real.num_features
+        self.weight = torch.ones(Cp, device=dev)
+        self.bias = torch.zeros(Cp, device=dev)
+        self.running_mean = torch.zeros(Cp, device=dev)
+        self.running_var = torch.ones(Cp, device=dev)
+
+    training = property(lambda self: self.real.training)
+    momentum = property(lambda self: self.real.momentum)
+    eps = property(lambda self: self.real.eps)
+    track_running_stats = property(lambda self: self.real.track_running_stats)
+    num_batches_tracked = property(lambda self: self.real.num_batches_tracked)
+
+    def pull(self):
+        r, C = self.real, self.C
+        with torch.no_grad():
+            if r.weight is not None:
+                self.weight[:C].copy_(r.weight)
+                self.bias[:C].copy_(r.bias)
+            self.running_mean[:C].copy_(r.running_mean)
+            self.running_var[:C].copy_(r.running_var)
+
+    def push_stats(self):
+        with torch.no_grad():
+            self.real.running_mean.copy_(self.running_mean[:self.C])
+            self.real.running_var.copy_(self.running_var[:self.C])
+
+
+def _gs_padded_params(m, Cp):
+    """Persistent zero-padded copies of the gate's parameters, refreshed in place when the real ones moved."""
+    from . import engine
+    gc = m._gate_conv
+    c1, c3 = gc[1], gc[3]
+    C1 = c1.weight.shape[0]
+    dev = c1.weight.device
+    ent = getattr(m, "_saunet_pad", None)
+    if ent is None or ent["dev"] != dev or ent["Cp"] != Cp:
+        ent = {"dev": dev, "Cp": Cp, "gen": None, "bn0": _PadBN(gc[0], Cp),
+               "w1": torch.zeros(Cp, Cp, 1, 1, device=dev).requires_grad_(True), "b1": torch.zeros(Cp, device=dev).requires_grad_(True),
+               "w3": torch.zeros(1, Cp, 1, 1, device=dev).requires_grad_(True)}
+        m._saunet_pad = ent
+    gen = (engine.weight_generation(c1.weight), engine.weight_generation(c3.weight), c1.bias._version)
+    if ent["gen"] != gen or engine.FORCE_PACK:
+        with torch.no_grad():
+            ent["w1"][:C1, :C1].copy_(c1.weight)
+            ent["b1"][:C1].copy_(c1.bias)
+            ent["w3"][:, :C1].copy_(c3.weight)
+        ent["gen"] = gen
+    ent["bn0"].pull()
+    return ent
+
+
+def _scatter_grad(tp, padded, real, rows, cols, cols_pad):
+    """real.grad[rows, cols] += padded.grad[:rows, :cols] (row pitch cols_pad)."""
+    pg = tp.pgrads.get(padded)
+    if pg is not None and real is not None and real.requires_grad:
+        _C.call("saunet_copy_slice", pg.data_ptr(), cols_pad, tp.pgrad(real), cols, cols, rows, 1, tp.stream)
+
+
+def gsconv_body_padded(tp, m, x, g):
+    C = x.C
+    C1, Cp = C + 1, _round4(C + 1)
+    n = x.npix
+    B, H, W = x.B, x.H, x.W
+    xg = tp.new(B, H, W, Cp)
+    xg.s.t.zero_()                                  # the pad channels must be exactly zero
+    copy_slice(tp, x, xg.slice(0, C))
+    copy_slice(tp, g, xg.slice(C, 1))
+    xin = xg.slice(0, C)
+    gc = m._gate_conv
+    c1, c3, bn4m = gc[1], gc[3], _check_bn(gc[4])
+    _check_bn(gc[0])
+    P = _gs_padded_params(m, Cp)
+    bn0m, w1, b1, w3 = P["bn0"], P["w1"], P["b1"], P["w3"]
+    st0 = bn_stats_slot(tp, Cp) if (bn0m.training or not bn0m.track_running_stats) else None
+    if st0 is not None:
+        channel_stats(tp, xg, st0[0], st0[1])
+    bn0 = bn_finalize(tp, bn0m, Cp, st0, n)
+    if st0 is not None and bn0m.track_running_stats:
+        bn0m.push_stats()
+    h1, r1 = conv2d(tp, xg, w1, b1, pro=bn0, pro_relu=0, act=ACT_RELU)
+    st4 = _stat(tp, bn4m, 1)
+    a_pre, r3 = conv2d(tp, h1, w3, c3.bias, stat=st4)
+    bn4 = bn_finalize(tp, bn4m, 1, st4, n)
+    alphas = tp.new(B, H, W, 1)
+    affine_act(tp, a_pre, bn4.state, alphas, ACT_SIGMOID)
+    out, rmain = conv2d(tp, xin, m.weight, None, row_scale=alphas.ptr, row_add=1.0)
+
+    def bwd():
+        dout, dal_ext = tp.grad(out), tp.grad(alphas)
+        if dout is None and dal_ext is None:
+            return
+        dalpha = tp.new(B, H, W, 1)
+        du = None
+        if dout is not None:
+            du = tp.new(B, H, W, C)
+            _C.call("saunet_rowscale_bwd", dout.ptr, dout.ld, out.ptr, out.ld, alphas.ptr, C, n, du.ptr, du.ld,
+                    dalpha.ptr, 0, tp.stream)
+            if dal_ext is not None:
+                copy_slice(tp, dal_ext, dalpha, 1)
+        else:
+            copy_slice(tp, dal_ext, dalpha, 0)
+        act_bwd(tp, dalpha, alphas, dalpha, ACT_SIGMOID)
+        bn_backward(tp, bn4, dalpha, a_pre, None, ACT_NONE, dalpha, 0)
+        dh1 = tp.new(B, H, W, Cp)
+        conv2d_bwd(tp, r3, dalpha, dh1, 0)
+        act_bwd(tp, dh1, h1, dh1, ACT_RELU)
+        da0 = tp.new(B, H, W, Cp)
+        conv2d_bwd(tp, r1, dh1, da0, 0)
+        gxg, acc = tp.gw(xg)
+        bn_backward(tp, bn0, da0, xg, None, ACT_NONE, gxg, acc)
+        if du is not None:
+            conv2d_bwd(tp, rmain, du, gxg.slice(0, C), 1)
+        # gradients of the padded copies -> the real parameters
+        _scatter_grad(tp, w1, c1.weight, C1, C1, Cp)
+        _scatter_grad(tp, b1, c1.bias, 1, C1, Cp)
+        _scatter_grad(tp, w3, c3.weight, 1, C1, Cp)
+        _scatter_grad(tp, bn0m.weight, bn0m.real.weight, 1, C1, Cp)
+        _scatter_grad(tp, bn0m.bias, bn0m.real.bias, 1, C1, Cp)
+        gx, a = tp.gw(x)
+        copy_slice(tp, gxg.slice(0, C), gx, a)
+        gg, a = tp.gw(g)
+        copy_slice(tp, gxg.slice(C, 1), gg, a)
+    tp.on_backward(bwd)
+    return out, alphas
+
+
 def gsconv_body(tp, m, x, g):
     """-> (out, alphas).  x: [.,C], g: [.,1].  Zero-copy when g is the channel right after x in one Store."""
+    from . import engine
+    if (x.C + 1) % 4 and x.C + 1 >= GS_PAD_MIN and engine.get_precision() != "fp32" and m.bias is None \
+            and tuple(m.kernel_size) == (1, 1) and g.C == 1 and x.C % 4 == 0:
+        return gsconv_body_padded(tp, m, x, g)
     if m.bias is not None or tuple(m.kernel_size) != (1, 1) or tuple(m.stride) != (1, 1) or tuple(m.padding) != (0, 0) \
             or tuple(m.dilation) != (1, 1) or m.groups != 1:
         raise NotImplementedError("saunet_b200 GatedSpatialConv2d: only the 1x1 / stride 1 / no-bias form used by "
