@@ -61,7 +61,8 @@ extern "C" int saunet_conv2d_fwd(const saunet_conv_desc* d, void* stream) {
                          "tiles, statistics targets, and no bias / row scale / activation");
         return conv_fwd_pw_t(d, (cudaStream_t)stream);
     }
-    if (conv_skinny_eligible(d)) return conv_fwd_skinny(d, (cudaStream_t)stream);
+    const bool prefer_tc = SAUNET_ENV_FLAG("SAUNET_PREFER_TC") && d->w_tc && d->Cin >= 32 && d->Cout >= 32;
+    if (conv_skinny_eligible(d) && !prefer_tc) return conv_fwd_skinny(d, (cudaStream_t)stream);
     if (conv_halo_tma_eligible(d)) return conv_fwd_halo_tma(d, (cudaStream_t)stream);      // 3x3: TMA-fed persistent halo kernel
     SAUNET_CHECK_ARG(!d->tc_cm, SAUNET_ERR_BAD_SHAPE, "conv2d_fwd: chunk-major padded weights (tc_cm) given for a geometry the TMA halo kernel does not take");
     if (conv_halo_eligible(d) && !SAUNET_ENV_FLAG("SAUNET_NO_HALO")) return conv_fwd_halo(d, (cudaStream_t)stream);

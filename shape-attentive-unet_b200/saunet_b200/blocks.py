@@ -129,7 +129,8 @@ def basic_block_body(tp, m, x, out=None):
 # block's only real arithmetic (2(C+1)^2 FLOP per pixel); with an odd channel count it can only run on the scalar FFMA
 # kernels (257 -> 257 at 128x128, batch 32: 6.5 ms forward, 9.2 ms weight gradient).  Zero channels / zero weight rows and
 # columns change nothing mathematically and put the three gate convolutions on the tensor-core kernels.
-GS_PAD_MIN = 41          # pad when C+1 >= this (smaller gates: the per-pixel skinny kernels are as fast)
+import os as _os
+GS_PAD_MIN = int(_os.environ.get('SAUNET_GS_PAD_MIN', '41'))          # pad when C+1 >= this (smaller gates: the per-pixel skinny kernels are as fast)
 
 
 class _PadBN:
