@@ -86,7 +86,9 @@ def conv_bn_relu_body(tp, seq, x, out=None, pad=None):
         dt = tp.new(t.B, t.H, t.W, Co)
         bn_backward(tp, bn, dout, t, out, ACT_RELU, dt, 0)
         dx, acc = tp.gw(x)
-        conv2d_bwd(tp, r, dt, dx, acc)
+        # a bias in front of a train-mode BatchNorm has an exactly zero gradient (the BN gradient sums to zero over the
+        # batch): skip the extra column-sum pass over dt (the reference computes ~1e-7 of round-off there)
+        conv2d_bwd(tp, r, dt, dx, acc, need_bias=not bn.training)
     tp.on_backward(bwd)
     return out
 
@@ -242,7 +244,7 @@ def gsconv_body_padded(tp, m, x, g):
         act_bwd(tp, dalpha, alphas, dalpha, ACT_SIGMOID)
         bn_backward(tp, bn4, dalpha, a_pre, None, ACT_NONE, dalpha, 0)
         dh1 = tp.new(B, H, W, Cp)
-        conv2d_bwd(tp, r3, dalpha, dh1, 0)
+        conv2d_bwd(tp, r3, dalpha, dh1, 0, need_bias=not bn4.training)
         act_bwd(tp, dh1, h1, dh1, ACT_RELU)
         da0 = tp.new(B, H, W, Cp)
         conv2d_bwd(tp, r1, dh1, da0, 0)
@@ -318,7 +320,7 @@ def gsconv_body(tp, m, x, g):
         act_bwd(tp, dalpha, alphas, dalpha, ACT_SIGMOID)
         bn_backward(tp, bn4, dalpha, a_pre, None, ACT_NONE, dalpha, 0)
         dh1 = tp.new(B, H, W, C + 1)
-        conv2d_bwd(tp, r3, dalpha, dh1, 0)
+        conv2d_bwd(tp, r3, dalpha, dh1, 0, need_bias=not bn4.training)
         act_bwd(tp, dh1, h1, dh1, ACT_RELU)
         da0 = tp.new(B, H, W, C + 1)
         conv2d_bwd(tp, r1, dh1, da0, 0)
@@ -417,12 +419,12 @@ def dual_att_body(tp, m, lo, skip, mcat=None):
         # c3x3rb
         bn_backward(tp, bnc, dfused, tc, fused, ACT_RELU, dfused, 0)
         gm, acc = tp.gw(mcat)
-        conv2d_bwd(tp, rc, dfused, gm, acc)
+        conv2d_bwd(tp, rc, dfused, gm, acc, need_bias=not bnc.training)
         # mrf.up
         dtu = tp.new(B, H, W, C0)
         bn_backward(tp, bnu, gm.slice(C1, C0), tu, up, ACT_RELU, dtu, 0)
         dlo, acc = tp.gw(lo)
-        convT4_bwd(tp, lo, ct.weight, ct.bias, dtu, dlo, acc)
+        convT4_bwd(tp, lo, ct.weight, ct.bias, dtu, dlo, acc, need_bias=not bnu.training)
         if copied:
             gs, a = tp.gw(skip)
             copy_slice(tp, gm.slice(0, C1), gs, a)
@@ -454,7 +456,7 @@ def decoder_block_body(tp, m, x, out=None):
         dt2 = tp.new(B, H, W, Co)
         bn_backward(tp, bnt, dout, t2, out, ACT_RELU, dt2, 0)
         da1, acc = tp.gw(a1)
-        convT4_bwd(tp, a1, ct.weight, ct.bias, dt2, da1, acc)
+        convT4_bwd(tp, a1, ct.weight, ct.bias, dt2, da1, acc, need_bias=not bnt.training)
     tp.on_backward(bwd)
     return out
 
@@ -500,7 +502,7 @@ def dense_block_body(tp, blk, X, c_in, sums):
             conv2d_bwd(tp, r2, gX.slice(cin, gr), da2, 0)
             bn_backward(tp, bn2, da2, t1, None, ACT_RELU, da2, 0)
             if bn_dgrad_fused_ok(r1, da2):
-                conv2d_bwd(tp, r1, da2, None)
+                conv2d_bwd(tp, r1, da2, None, async_wgrad=True)
                 bn_dgrad_fused(tp, r1, da2, gX.slice(0, cin), 1)
             else:
                 da1 = tp.new(B, H, W, cin)
@@ -525,7 +527,7 @@ def transition_body(tp, tr, X, sums, out):
         dtt = tp.new(tt.B, tt.H, tt.W, tt.C)
         _C.call("saunet_avgpool2_bwd", dout.ptr, dout.ld, tt.B, tt.H, tt.W, tt.C, dtt.ptr, dtt.ld, 0, tp.stream)
         if bn_dgrad_fused_ok(r, dtt):
-            conv2d_bwd(tp, r, dtt, None)
+            conv2d_bwd(tp, r, dtt, None, async_wgrad=True)
             gX, acc = tp.gw(X)
             bn_dgrad_fused(tp, r, dtt, gX, acc)      # mean terms settled per slice by the dense block's backward
         else:

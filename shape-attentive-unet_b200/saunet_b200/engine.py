@@ -11,6 +11,7 @@ torch is used here for device memory (caching allocator), the current stream
 and the autograd boundary -- never for arithmetic on the path.  There is no CPU
 fallback: a non-CUDA tensor or a missing library raises.
 """
+import contextlib
 import ctypes
 import os
 import weakref
@@ -22,6 +23,12 @@ from ._C import ACT_NONE, ACT_RELU, ACT_SIGMOID, ConvDesc, WgradDesc
 
 BN_EPS = 1e-5
 OVERLAP = os.environ.get("SAUNET_OVERLAP", "1") == "1"      # post-process gradient buckets on a side stream during backward
+# Small problems (DenseNet blocks 3-4, the deep decoder stages: <= 128 tiles on 148 SMs, 15-30 us per launch whatever the
+# size) leave most of the GPU idle; independent launches -- the weight gradient and the data gradient of one conv -- are
+# therefore issued on different streams so that they share it.  SAUNET_CONCURRENCY=0 serialises everything again.
+CONCURRENCY = os.environ.get("SAUNET_CONCURRENCY", "1") == "1"
+ASYNC_WGRAD_MAX_PIX = int(os.environ.get("SAUNET_ASYNC_WGRAD_MAX_PIX", str(1 << 40)))     # (measured: every size gains; 50.5 -> 46.7 ms/step)
+_SIDE_STREAMS = {}
 
 
 def _round4(n):
@@ -90,7 +97,41 @@ class Tape:
         self.arena = None
         self.used_packed = False
         self._touch, self._cur = None, 0
+        self._dirty, self._hold, self._wg_rr = set(), [], 0
         self.repacked = []      # pack-cache entries refreshed under FORCE_PACK by this tape (flag reset at the end)
+
+    # ---- streams --------------------------------------------------------
+    @contextlib.contextmanager
+    def on_side(self, k, hold=()):
+        """Issue the enclosed launches on side stream ``k``, ordered after everything issued so far on the current
+        stream.  ``hold``: objects (Stores) the side work reads that must stay alive until the next ``join_sides``."""
+        if not CONCURRENCY:
+            yield
+            return
+        cur = torch.cuda.current_stream(self.device)
+        key = (self.device.index, k)
+        s = _SIDE_STREAMS.get(key)
+        if s is None:
+            s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=self.device)
+        s.wait_stream(cur)
+        self._hold.extend(hold)
+        prev = self.stream
+        with torch.cuda.stream(s):
+            self.stream = s.cuda_stream
+            try:
+                yield
+            finally:
+                self.stream = prev
+        self._dirty.add(k)
+
+    def join_sides(self):
+        """The current stream waits for all side-stream work issued since the last join."""
+        if self._dirty:
+            cur = torch.cuda.current_stream(self.device)
+            for k in self._dirty:
+                cur.wait_stream(_SIDE_STREAMS[(self.device.index, k)])
+            self._dirty.clear()
+        self._hold.clear()
 
     # ---- memory ---------------------------------------------------------
     def new(self, B, H, W, C, ld=None):
@@ -192,8 +233,10 @@ class Tape:
             self._cur = i
             fn()
             if sched is not None and i in sched:
+                self.join_sides()                  # weight gradients issued on side streams belong to the bucket too
                 for b in sched[i]:
                     arena.bucket_ready(b)
+        self.join_sides()
         self.ops = []
         if arena is not None:
             if sched is None:
@@ -506,20 +549,30 @@ def conv2d(tp, x, w, b, y=None, stride=1, pad=0, pro=None, pro_relu=0, act=ACT_N
     return y, r
 
 
-def conv2d_bwd(tp, r, dy, dx=None, dx_acc=0, need_bias=True):
+def conv2d_bwd(tp, r, dy, dx=None, dx_acc=0, need_bias=True, async_wgrad=None):
     """Given dy = d loss / d (conv output incl. bias): weight grad, bias grad and (if dx given) data grad
     w.r.t. the PROLOGUE OUTPUT (i.e. the activated tensor the GEMM consumed)."""
     w, x = r.w, r.x
     Cout, Cin, KH, KW = w.shape
     if w.requires_grad:
         pk = tp.packed_grad(w)
-        dwp = None if pk else torch.zeros(w.numel(), dtype=torch.float32, device=tp.device)
-        wgrad(tp, dy, x, pk or dwp.data_ptr(), KH, KW, dy.H, dy.W, sy=r.stride, sx=r.stride, offy=-r.pad, offx=-r.pad,
-              pro=r.pro.state if r.pro is not None else 0, pro_relu=r.pro_relu)
-        if not pk:
-            _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cout, Cin, KH, KW, 1, tp.stream)
-    if r.b is not None and r.b.requires_grad and need_bias:
-        bias_grad(tp, dy, r.b)
+        # the weight gradient only reads dy and x and writes its own packed image: small problems run it beside the data
+        # gradient on a side stream (round-robin over two) instead of in front of it
+        side = (dx is not None if async_wgrad is None else async_wgrad) and dy.npix <= ASYNC_WGRAD_MAX_PIX
+        ctx = tp.on_side(1 + (tp._wg_rr & 1), hold=(dy.s, x.s)) if side else contextlib.nullcontext()
+        if side:
+            tp._wg_rr += 1
+        with ctx:
+            dwp = None if pk else torch.zeros(w.numel(), dtype=torch.float32, device=tp.device)
+            wgrad(tp, dy, x, pk or dwp.data_ptr(), KH, KW, dy.H, dy.W, sy=r.stride, sx=r.stride, offy=-r.pad, offx=-r.pad,
+                  pro=r.pro.state if r.pro is not None else 0, pro_relu=r.pro_relu)
+            if not pk:
+                _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cout, Cin, KH, KW, 1, tp.stream)
+    if r.b is not None and r.b.requires_grad:
+        if need_bias:
+            bias_grad(tp, dy, r.b)
+        else:
+            tp.pgrad(r.b)             # analytically zero: the (zero-initialised) gradient still exists
     if dx is not None:
         if r.stride != 1:
             raise RuntimeError("saunet_b200: data gradient of a strided conv is not on the SAUNet path")
@@ -586,7 +639,7 @@ def convT4(tp, x, w, b, y, stat=None):
                  wtc=packed_tc(tp, w, 2, 4, Cin, Cout, phase=ph) if _tc_ok(x, Cout, K) else None)
 
 
-def convT4_bwd(tp, x, w, b, dy, dx, dx_acc):
+def convT4_bwd(tp, x, w, b, dy, dx, dx_acc, need_bias=True):
     Cin, Cout, _, _ = w.shape
     if w.requires_grad:
         pk = tp.packed_grad(w)
@@ -595,7 +648,10 @@ def convT4_bwd(tp, x, w, b, dy, dx, dx_acc):
         if not pk:
             _C.call("saunet_unpack_wgrad", dwp.data_ptr(), tp.pgrad(w), Cin, Cout, 4, 4, 1, tp.stream)
     if b is not None and b.requires_grad:
-        bias_grad(tp, dy, b)
+        if need_bias:
+            bias_grad(tp, dy, b)
+        else:
+            tp.pgrad(b)
     if dx is not None:
         conv(tp, dy, packed(tp, w, 0), Cin, 4, 4, dx, x.H, x.W, sy=2, sx=2, offy=-1, offx=-1, acc=dx_acc,
              wtc=packed_tc(tp, w, 0, 16, Cout, Cin) if _tc_ok(dy, Cin, 16 * Cout) else None)
