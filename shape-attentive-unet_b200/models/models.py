@@ -284,51 +284,61 @@ class SAUNet(nn.Module):
             bn_backward(tp, bn5, g, X4, None, ACT_NONE, gX, acc)
         tp.on_backward(bwd_norm5)
 
-        # ---- shape stream (:337-356) ----
-        d0o = conv_op(tp, conv2, self.d0.weight, self.d0.bias)
-        ss = bilinear(tp, d0o, tp.new(B, H, W, d0o.C))
-        ss = basic_block_body(tp, self.res1, ss)
-        gates = []
-        for dconv, cconv, feat, gate, res in ((self.d1, self.c3, conv3, self.gate1, self.res2),
-                                              (self.d2, self.c4, conv4, self.gate2, self.res3),
-                                              (self.d3, self.c5, conv5, self.gate3, None)):
-            C = dconv.weight.shape[0]
-            xg = tp.new(B, H, W, C + 1, ld=_round4(C + 1))
-            conv_op(tp, ss, dconv.weight, dconv.bias, y=xg.slice(0, C))
-            clo = conv_op(tp, feat, cconv.weight, cconv.bias)
-            bilinear(tp, clo, xg.slice(C, 1))
-            ss, alphas = gsconv_body(tp, gate, xg.slice(0, C), xg.slice(C, 1))
-            gates.append(alphas)
-            if res is not None:
-                ss = basic_block_body(tp, res, ss)
-        # fuse -> (identity resize, :355) -> sigmoid
-        edge_out = conv_op(tp, ss, self.fuse.weight, self.fuse.bias, act=ACT_SIGMOID)
-        # ---- Canny fusion (:358-369): on-device, non-differentiable ----
-        ec = tp.new(B, H, W, 2)
-        cat_copy(tp, edge_out, ec.slice(0, 1))
-        canny = tp.new(B, H, W, 1)
-        nbytes = _C.load().saunet_canny_workspace_bytes(B, H, W)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=tp.device)
-        _C.call("saunet_canny_fwd", x_nchw.data_ptr(), B, x_nchw.shape[1], H, W, 10, 100, canny.ptr, ws.data_ptr(),
-                nbytes, tp.stream)
-        engine.copy_slice(tp, canny, ec.slice(1, 1))
-        acts = conv_op(tp, ec, self.cw.weight, self.cw.bias, act=ACT_SIGMOID)
+        # The shape stream (everything at 256x256: HBM-shaped, latency-bound launches) and the decoder (tensor-bound, small
+        # grids in its deep stages) are independent until dec0 reads cat[dec1, edge]: the forward issues the shape stream
+        # on a side stream so the two share the GPU, and so does the backward (Tape.side_section: gradients the shape
+        # stream accumulates into the shared encoder features go to private buffers folded in at the join).  D0 is
+        # allocated first, on the main stream, because both write a slice of it.
         nf = self.expand[0].weight.shape[0]
         dec1_C = self.dec1.block[1].weight.shape[1]
         D0 = tp.new(B, H, W, dec1_C + nf)
-        conv_bn_relu_body(tp, self.expand, acts, out=D0.slice(dec1_C, nf))
+        with tp.side_section(3):
+            # ---- shape stream (:337-356) ----
+            d0o = conv_op(tp, conv2, self.d0.weight, self.d0.bias)
+            ss = bilinear(tp, d0o, tp.new(B, H, W, d0o.C))
+            ss = basic_block_body(tp, self.res1, ss)
+            gates = []
+            for dconv, cconv, feat, gate, res in ((self.d1, self.c3, conv3, self.gate1, self.res2),
+                                                  (self.d2, self.c4, conv4, self.gate2, self.res3),
+                                                  (self.d3, self.c5, conv5, self.gate3, None)):
+                C = dconv.weight.shape[0]
+                xg = tp.new(B, H, W, C + 1, ld=_round4(C + 1))
+                conv_op(tp, ss, dconv.weight, dconv.bias, y=xg.slice(0, C))
+                clo = conv_op(tp, feat, cconv.weight, cconv.bias)
+                bilinear(tp, clo, xg.slice(C, 1))
+                ss, alphas = gsconv_body(tp, gate, xg.slice(0, C), xg.slice(C, 1))
+                gates.append(alphas)
+                if res is not None:
+                    ss = basic_block_body(tp, res, ss)
+            # fuse -> (identity resize, :355) -> sigmoid
+            edge_out = conv_op(tp, ss, self.fuse.weight, self.fuse.bias, act=ACT_SIGMOID)
+            # ---- Canny fusion (:358-369): on-device, non-differentiable ----
+            ec = tp.new(B, H, W, 2)
+            cat_copy(tp, edge_out, ec.slice(0, 1))
+            canny = tp.new(B, H, W, 1)
+            nbytes = _C.load().saunet_canny_workspace_bytes(B, H, W)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=tp.device)
+            _C.call("saunet_canny_fwd", x_nchw.data_ptr(), B, x_nchw.shape[1], H, W, 10, 100, canny.ptr, ws.data_ptr(),
+                    nbytes, tp.stream)
+            engine.copy_slice(tp, canny, ec.slice(1, 1))
+            acts = conv_op(tp, ec, self.cw.weight, self.cw.bias, act=ACT_SIGMOID)
+            conv_bn_relu_body(tp, self.expand, acts, out=D0.slice(dec1_C, nf))
         # ---- decoder (:372-384) ----
-        center = conv_bn_relu_body(tp, self.center, maxpool2(tp, conv5))
-        dec, atts = center, []
-        for blk, skip_src, M in ((self.dec5, None, M5), (self.dec4, conv4, None), (self.dec3, conv3, None),
-                                 (self.dec2, conv2, None)):
-            if M is None:
-                M = tp.new(B, 2 * skip_src.H, 2 * skip_src.W, skip_src.C + dec.C)
-                bilinear(tp, skip_src, M.slice(0, skip_src.C))
-            skip = M.slice(0, M.C - dec.C)
-            dec, att = dual_att_body(tp, blk, dec, skip, mcat=M)
-            atts.append(att)
-        decoder_block_body(tp, self.dec1, dec, out=D0.slice(0, dec1_C))
+        def decoder_chain():
+            center = conv_bn_relu_body(tp, self.center, maxpool2(tp, conv5))
+            dec, atts = center, []
+            for blk, skip_src, M in ((self.dec5, None, M5), (self.dec4, conv4, None), (self.dec3, conv3, None),
+                                     (self.dec2, conv2, None)):
+                if M is None:
+                    M = tp.new(B, 2 * skip_src.H, 2 * skip_src.W, skip_src.C + dec.C)
+                    bilinear(tp, skip_src, M.slice(0, skip_src.C))
+                skip = M.slice(0, M.C - dec.C)
+                dec, att = dual_att_body(tp, blk, dec, skip, mcat=M)
+                atts.append(att)
+            decoder_block_body(tp, self.dec1, dec, out=D0.slice(0, dec1_C))
+            return atts
+        atts = decoder_chain()
+        tp.join_sides()                  # (the shape stream above ran on a side stream, see below)
         dec0 = conv_bn_relu_body(tp, self.dec0, D0)
         x_out = conv_op(tp, dec0, self.final.weight, self.final.bias)
         outs = [x_out, edge_out]

@@ -37,10 +37,10 @@ def _round4(n):
 
 class Store:
     """One NHWC allocation [npix, ld] plus (lazily) its gradient twin."""
-    __slots__ = ("t", "g", "ld", "npix", "ab")
+    __slots__ = ("t", "g", "ld", "npix", "ab", "tag")
 
-    def __init__(self, t, npix, ld):
-        self.t, self.g, self.ld, self.npix = t, None, ld, npix
+    def __init__(self, t, npix, ld, tag=0):
+        self.t, self.g, self.ld, self.npix, self.tag = t, None, ld, npix, tag
         self.ab = 0          # device pointer of double[2][ld]: pending BatchNorm-backward mean terms (see bn_dgrad_fused)
 
 
@@ -88,8 +88,7 @@ class Tape:
         self.stream = torch.cuda.current_stream(device).cuda_stream
         self.ops = []
         self.pgrads = {}
-        self._dchunk = None
-        self._doff = 0
+        self._dchunks = {}
         self._fchunk = None
         self._foff = 0
         self._keep = []
@@ -98,9 +97,32 @@ class Tape:
         self.used_packed = False
         self._touch, self._cur = None, 0
         self._dirty, self._hold, self._wg_rr = set(), [], 0
+        self._tag, self._open_sections = 0, []          # forward: tag new Stores / ops are registered with; sections awaiting their join
+        self._exec_tag, self._fork_ev, self._priv = 0, {}, {}     # backward: tag of the running op, fork events, private grad buffers
         self.repacked = []      # pack-cache entries refreshed under FORCE_PACK by this tape (flag reset at the end)
 
     # ---- streams --------------------------------------------------------
+    @contextlib.contextmanager
+    def side_section(self, k):
+        """A forward SECTION on side stream ``k`` whose backward ops also run on that stream, concurrently with the
+        backward of whatever the main stream ran between the end of this section and the next ``join_sides()``:
+        the reverse of the forward join is the backward fork (an event on the main stream the side stream waits for),
+        the reverse of the forward fork is the backward join.  Gradients the section's backward accumulates into
+        tensors created OUTSIDE it (shared encoder features) go to private zero-initialised buffers that the backward
+        join adds into the real gradients, so the two streams never read-modify-write the same memory."""
+        if not CONCURRENCY:
+            yield
+            return
+        if self.record:
+            self.ops.append(("join", k))
+        prev_tag, self._tag = self._tag, k
+        self._open_sections.append(k)
+        try:
+            with self.on_side(k):
+                yield
+        finally:
+            self._tag = prev_tag
+
     @contextlib.contextmanager
     def on_side(self, k, hold=()):
         """Issue the enclosed launches on side stream ``k``, ordered after everything issued so far on the current
@@ -126,6 +148,11 @@ class Tape:
 
     def join_sides(self):
         """The current stream waits for all side-stream work issued since the last join."""
+        if self._open_sections and self.record and self._tag == 0:
+            for k in self._open_sections:
+                self.ops.append(("fork", k))
+        if self._tag == 0:
+            self._open_sections = []
         if self._dirty:
             cur = torch.cuda.current_stream(self.device)
             for k in self._dirty:
@@ -137,21 +164,23 @@ class Tape:
     def new(self, B, H, W, C, ld=None):
         ld = C if ld is None else ld
         t = torch.empty(B * H * W * ld, dtype=torch.float32, device=self.device)
-        return Buf(Store(t, B * H * W, ld), 0, C, B, H, W)
+        return Buf(Store(t, B * H * W, ld, self._tag), 0, C, B, H, W)
 
     def wrap(self, t, B, H, W, C):
         """Adopt an existing contiguous [B,H,W,C] fp32 tensor."""
         return Buf(Store(t, B * H * W, C), 0, C, B, H, W)
 
     def dzeros(self, n):
-        """n zeroed doubles -> device pointer (arena; one memset per chunk)."""
+        """n zeroed doubles -> device pointer (arena; one memset per chunk).  Chunks are per stream: the memset that
+        zeroes a chunk is ordered only with the stream it was issued on."""
         n = (n + 1) // 2 * 2
-        if self._dchunk is None or self._doff + n > self._dchunk.numel():
-            self._dchunk = torch.zeros(max(1 << 15, n), dtype=torch.float64, device=self.device)
-            self._keep.append(self._dchunk)
-            self._doff = 0
-        p = self._dchunk.data_ptr() + 8 * self._doff
-        self._doff += n
+        ent = self._dchunks.get(self.stream)
+        if ent is None or ent[1] + n > ent[0].numel():
+            t = torch.zeros(max(1 << 15, n), dtype=torch.float64, device=self.device)
+            self._keep.append(t)
+            ent = self._dchunks[self.stream] = [t, 0]
+        p = ent[0].data_ptr() + 8 * ent[1]
+        ent[1] += n
         return p
 
     def fempty(self, n):
@@ -180,6 +209,15 @@ class Tape:
         """Gradient write target for ``buf`` -> (gbuf, accumulate_flag).
         First write covering the whole Store skips the zero fill."""
         s = buf.s
+        if self._exec_tag and s.tag != self._exec_tag:
+            # an op of a side section accumulating into a tensor it shares with the main stream: private buffer
+            key = (id(s), buf.c0, buf.C)
+            ent = self._priv.get(key)
+            if ent is None:
+                t = torch.zeros(buf.npix * buf.C, dtype=torch.float32, device=self.device)
+                self._keep.append(t)
+                ent = self._priv[key] = (Buf(Store(t, buf.npix, buf.C, self._exec_tag), 0, buf.C, buf.B, buf.H, buf.W), buf, self._exec_tag)
+            return ent[0], 1
         if s.g is None:
             if buf.full():
                 s.g = Store(torch.empty(s.npix * s.ld, dtype=torch.float32, device=self.device), s.npix, s.ld)
@@ -231,7 +269,13 @@ class Tape:
         self._touch = {} if (arena is not None and sched is None) else None
         for i, fn in enumerate(reversed(self.ops)):
             self._cur = i
-            fn()
+            if isinstance(fn, tuple):
+                if isinstance(fn[0], str):
+                    self._run_marker(*fn)
+                else:
+                    self._run_tagged(*fn)
+            else:
+                fn()
             if sched is not None and i in sched:
                 self.join_sides()                  # weight gradients issued on side streams belong to the bucket too
                 for b in sched[i]:
@@ -250,7 +294,46 @@ class Tape:
 
     def on_backward(self, fn):
         if self.record:
-            self.ops.append(fn)
+            self.ops.append((fn, self._tag) if self._tag else fn)
+
+    def _run_marker(self, kind, k):
+        """Backward of the forward fork / join of side section ``k`` (see side_section)."""
+        cur = torch.cuda.current_stream(self.device)
+        if kind == "fork":                       # reverse of the forward join: the side stream may start from here
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._fork_ev[k] = ev
+            return
+        # "join": reverse of the forward fork -- wait for the section's backward, then fold its private gradient buffers
+        side = _SIDE_STREAMS.get((self.device.index, k))
+        if side is not None:
+            cur.wait_stream(side)
+        self._dirty.discard(k)
+        for key in [key for key, ent in self._priv.items() if ent[2] == k]:
+            pb, orig, _ = self._priv.pop(key)
+            dst, acc = self.gw(orig)
+            copy_slice(self, pb, dst, acc)
+
+    def _run_tagged(self, fn, k):
+        """Run a backward op of side section ``k`` on its stream, ordered after the section's fork event only."""
+        side = _SIDE_STREAMS.get((self.device.index, k))
+        ev = self._fork_ev.get(k)
+        if side is None or ev is None:           # (forward ran without concurrency): plain execution
+            fn()
+            return
+        if ev is not True:
+            side.wait_event(ev)
+            self._fork_ev[k] = True              # waited once: later ops of the section are ordered by the stream itself
+        prev = self.stream
+        with torch.cuda.stream(side):
+            self.stream = side.cuda_stream
+            self._exec_tag = self._tag = k       # (temporaries the op allocates belong to the section too)
+            try:
+                fn()
+            finally:
+                self._exec_tag = self._tag = 0
+                self.stream = prev
+        self._dirty.add(k)
 
 
 # ---------------------------------------------------------------------------
