@@ -46,12 +46,17 @@ SIZE = 256
 REF_SAMPLE = 4                     # slices per CPU step: the bounded sample of the batch-16 workload the CPU arms time
 
 
-def workload_config(B, world, workload="train", extra=None):
+ARITH = {"f32": "fp32-class 3xTF32 arithmetic",
+         "bf16": "bf16 tensor-core operands (kind::f16) with fp32 accumulation for every forward / data-gradient convolution, "
+                 "single-pass TF32 weight gradients; fp32 activations in HBM, fp32 BatchNorm statistics, loss, master weights"}
+
+
+def workload_config(B, world, workload="train", extra=None, dtype="f32"):
     """`config` of the JSON line -- shared by both arms so that the driver compares like with like."""
     names = {"train": "SAUNet fwd+DualLoss+bwd, batch %d/GPU, 256x256x3 fp32 slices -> 4 classes, train-mode BN, on-device Canny "
-                      "(BASELINE configs[1])" % B,
+                      "(BASELINE configs[1]%s)" % (B, "" if dtype == "f32" else "; " + ARITH[dtype]),
              "train_loop": "SAUNet training loop: fwd+DualLoss+bwd+gradient all-reduce+fused optimizer step, batch %d/GPU, 256x256x3 "
-                           "slices -> 4 classes, train-mode BN (BASELINE configs[2] shape; fp32-class 3xTF32 arithmetic)" % B}
+                           "slices -> 4 classes, train-mode BN (BASELINE configs[2]; %s)" % (B, ARITH[dtype])}
     c = {"workload": names[workload], "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
          "l2": "per-step working set (activations >> 126 MB L2) exceeds L2; no explicit flush"}
     if extra:
@@ -141,6 +146,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _C.load()
+    from saunet_b200 import engine
+    engine.set_precision("bf16" if args.dtype == "bf16" else "3xtf32")
     B = args.batch
     seg_mod, unet, arena = build_ours(dev, B)
     hb = host_batch(B, rank)
@@ -206,7 +213,10 @@ def run_ours(args):
     if rank == 0:
         # three profiled steps; per C-ABI call the MEDIAN of its three timings is kept, so that a single slow launch
         # (allocator growth, a clock dip) cannot pick the "dominant kernel"
+        # (serialised: with the weight gradients / shape stream on side streams the bracketing events of one call
+        #  would span kernels of other streams sharing the SMs)
         runs = []
+        conc, engine.CONCURRENCY = engine.CONCURRENCY, False
         for _ in range(3):
             _C.PROFILE = []
             with arena.no_sync():                 # rank 0 only: NO collective may be issued in this pass
@@ -214,6 +224,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             prof, _C.PROFILE = _C.PROFILE, None
             runs.append([(name, a.elapsed_time(b), fl, nb, kern) for name, a, b, fl, nb, _tag, kern in prof])
+        engine.CONCURRENCY = conc
         agg, kagg = {}, {}
         if len({len(r) for r in runs}) == 1:
             calls = [(r0[0], sorted((r0[1], r1[1], r2[1]))[1], r0[2], r0[3], r0[4]) for r0, r1, r2 in zip(*runs)]
@@ -249,8 +260,11 @@ def run_ours(args):
                     "frac": round(ach / pk["tflops"], 4), "traffic": ncu[1] if ncu else None, "launches": cnt,
                     "avg_launch_ms": round(t_ms / cnt, 4), "share_of_step": round(t_ms / total, 3), "peak_src": pk["src"],
                     "all_conv_tflops": round(conv_fl / (conv_ms / 1e3) / 1e12, 2),
-                    "note": "peak = measured dense bf16 cuBLAS (sustained); this path computes fp32-class 3xTF32: 3 tf32 MMAs per "
-                            "product at half the bf16 rate, i.e. a ceiling of peak/6; `achieved` counts each product once"}
+                    "note": ("peak = measured dense bf16 cuBLAS (sustained); this path computes fp32-class 3xTF32: 3 tf32 MMAs per "
+                             "product at half the bf16 rate, i.e. a ceiling of peak/6; `achieved` counts each product once")
+                            if args.dtype == "f32" else
+                            ("peak = measured dense bf16 cuBLAS (sustained); forward / data-gradient convolutions run bf16 MMAs "
+                             "(ceiling = peak), weight gradients single-pass TF32 (ceiling = peak/2)")}
         else:
             ach = nb / (t_ms / 1e3) / 1e9
             roof = {"bound": "hbm", "kernel": kern, "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -302,9 +316,10 @@ def run_ours(args):
         h2d = sum(v.numel() * v.element_size() for v in hb.values())
         out = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
                "config": workload_config(B, world, args.workload,
-                                         {"optimizer": "fused " + args.optimizer} if args.workload == "train_loop" else None),
+                                         {"optimizer": "fused " + args.optimizer} if args.workload == "train_loop" else None,
+                                         dtype=args.dtype),
                "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                        "ms_per_step": round(ms_e2e / args.steps, 3),
                        "launch": "cuda_graph" if (graphed is not None and use_graph) else "eager"},
@@ -549,7 +564,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=None, help="slices per GPU (default 16; 32 for --dtype bf16 = BASELINE configs[2])")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="arithmetic of the convolutions: f32 = 3xTF32 (fp32 class, the headline), bf16 = bf16 operands / fp32 accumulate")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the e2e arm eagerly instead of through a CUDA graph")
@@ -558,6 +575,8 @@ def main():
     ap.add_argument("--torch-gpu-context", action="store_true",
                     help="also time the oracle's stock torch ops (cuDNN) on the GPU, allow_tf32 off and on: a context number, never the product path")
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 32 if args.dtype == "bf16" else 16
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "blocks":

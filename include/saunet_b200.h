@@ -70,7 +70,8 @@ typedef struct saunet_conv_desc {
     int accumulate;              /* y += result instead of y = result */
     double* stat_sum; double* stat_sumsq;
     /* tensor-core path (conv_tc.cu): weights tiled by saunet_pack_weights_tc for N tile tc_bn; tc_passes 3 = 3xTF32
-     * (fp32-class accuracy), 1 = single-pass TF32.  NULL w_tc (or an ineligible geometry: Cin % 4 != 0, unaligned
+     * (fp32-class accuracy), 1 = single-pass TF32, 16 = bf16 operands (kind::f16, fp32 accumulate; activations stay
+     * fp32 in memory and are rounded to bf16 on their way into shared memory).  NULL w_tc (or an ineligible geometry: Cin % 4 != 0, unaligned
      * x) selects the exact-fp32 FFMA kernel, which reads `w`. */
     const float* w_tc; int tc_bn; int tc_passes;
     /* 1: w_tc is the chunk-major PADDED image of saunet_pack_weights_tc_cm (k-blocks = (32-channel chunk, tap), last
@@ -97,7 +98,7 @@ typedef struct saunet_wgrad_desc {
     int KH, KW, Hg, Wg, sy, sx, offy, offx;
     const float* q_scale; const float* q_shift; int q_relu;
     float* dw;                   /* packed [KH*KW*Cb][Ca] */
-    int precision;               /* 0: exact fp32 FFMA;  1: tcgen05 3xTF32 (conv_wgrad_tc.cu) when the geometry allows */
+    int precision;               /* 0: exact fp32 FFMA;  1: tcgen05 3xTF32 when the geometry allows;  2: tcgen05 single-pass TF32 */
 } saunet_wgrad_desc;
 int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream);
 
@@ -108,7 +109,8 @@ int saunet_conv2d_wgrad(const saunet_wgrad_desc* d, void* stream);
  * unpack: w_grad[a][b][t] (+)= packed[(t,b)][a]  (mode 0 only). */
 int saunet_pack_weights(const float* w, float* packed, int A, int Bc, int KH, int KW, int mode, void* stream);
 /* tensor-core weight tiling: kn = packed [K][N] (any mode above, one phase for mode 2) ->
- * out[n_tile][k_block(32)][hi,lo][BN][32] in the UMMA K-major SWIZZLE_128B shared-memory image, tf32-split;
+ * out[n_tile][k_block(32)][hi,lo][BN][32] in the UMMA K-major SWIZZLE_128B shared-memory image, tf32-split
+ * (passes 3; passes 1: hi image only; passes 16: one bf16 image of 64-byte rows, SWIZZLE_64B, half the floats);
  * K = taps*Cin, where Cin is the channel count of the tensor the conv GATHERS (so dgrad passes Cout). */
 int saunet_tc_tile_n(int Cout);
 long long saunet_tc_packed_floats(int K, int N, int BN, int passes);

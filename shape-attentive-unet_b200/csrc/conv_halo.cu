@@ -38,10 +38,12 @@ constexpr int kHaloIters = (kHaloItems + kHaloProducers - 1) / kHaloProducers;  
 // weight ring is sized so that two CTAs fit in 227 KB.
 template <int BN, int NPASS>
 struct HaloCfg {
-    static constexpr int NOP = (NPASS == 3) ? 2 : 1;
+    using Op = Opnd<NPASS>;
+    static constexpr int NOP = Op::NOP;
     static constexpr int NBUF = 1;
-    static constexpr int PATCH = NOP * kPatchBytes;                  // one buffer
-    static constexpr int B_STAGE = NOP * BN * 128;
+    static constexpr int IMG = Op::BF ? kPatchBytes / 2 : kPatchBytes;   // one patch image (bf16: 64-byte rows)
+    static constexpr int PATCH = NOP * IMG;                          // one buffer
+    static constexpr int B_STAGE = NOP * BN * Op::ROW;
     static constexpr int B_SPACE = 111 * 1024 - NBUF * PATCH;
     static constexpr int NSTB_RAW = B_SPACE / B_STAGE;
     static constexpr int NSTB = NSTB_RAW > 4 ? 4 : NSTB_RAW;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
             const bool ok = it < kHaloItems && iy >= 0 && iy < d.Hin && ix >= 0 && ix < d.Win;
             g_off[i] = ok ? ((b * d.Hin + iy) * d.Win + ix) * d.x_ld + chunk * 4 : -1;
             const int pr = py * kPitch + px;
-            s_off[i] = (it < kHaloItems) ? ((uint32_t)pr * 128u + (uint32_t)((chunk ^ (pr & 7)) << 4)) : 0xFFFFFFFFu;
+            s_off[i] = (it < kHaloItems) ? Opnd<NPASS>::off(pr, chunk) : 0xFFFFFFFFu;
         }
         auto load_chunk = [&](int cc, float4 (&v)[kHaloIters]) {
 #pragma unroll
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
             }
             mbar_wait(patch_empty(buf), ph ^ 1u);
             uint8_t* hi_img = sgen + buf * Cfg::PATCH;
-            uint8_t* lo_img = hi_img + kPatchBytes;
+            uint8_t* lo_img = hi_img + Cfg::IMG;
 #pragma unroll
             for (int i = 0; i < kHaloIters; ++i) {
                 if (s_off[i] == 0xFFFFFFFFu) continue;
@@ -140,12 +142,7 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
                     tv.x = fmaf(tv.x, sc.x, sh.x); tv.y = fmaf(tv.y, sc.y, sh.y); tv.z = fmaf(tv.z, sc.z, sh.z); tv.w = fmaf(tv.w, sc.w, sh.w);
                     if (d.in_relu) { tv.x = fmaxf(tv.x, 0.f); tv.y = fmaxf(tv.y, 0.f); tv.z = fmaxf(tv.z, 0.f); tv.w = fmaxf(tv.w, 0.f); }
                 }
-                float4 hi = split_hi4(tv);
-                *reinterpret_cast<float4*>(hi_img + s_off[i]) = hi;
-                if (NPASS == 3) {
-                    float4 lo = split_lo4(tv, hi);
-                    *reinterpret_cast<float4*>(lo_img + s_off[i]) = lo;
-                }
+                Opnd<NPASS>::store(hi_img, lo_img, s_off[i], tv);
             }
             fence_proxy_async();
             __syncwarp();
@@ -237,27 +234,28 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
         tc_fence_before();
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            using Op = Opnd<NPASS>;
+            const uint32_t idesc = Op::idesc(BN);
+            const uint32_t idesc2 = Op::idesc(2 * BN);
             int kb = 0;
             for (int cc = 0; cc < p.nchunk; ++cc) {
                 const int buf = cc % Cfg::NBUF; const uint32_t pph = (cc / Cfg::NBUF) & 1;
                 mbar_wait(patch_full(buf), pph);
                 const uint32_t a_hi0 = sbase + buf * Cfg::PATCH;
-                const uint32_t a_lo0 = a_hi0 + kPatchBytes;
+                const uint32_t a_lo0 = a_hi0 + Cfg::IMG;
                 for (int tap = 0; tap < 9; ++tap, ++kb) {
                     const int s = kb % NSTB; const uint32_t ph = (kb / NSTB) & 1;
                     mbar_wait(b_full(s), ph);
                     tc_fence_after();
                     const int ky = tap / 3, kx = tap - ky * 3;
-                    const uint32_t shift = (uint32_t)(ky * kPitch + kx) * 128u;
+                    const uint32_t shift = (uint32_t)(ky * kPitch + kx) * Op::ROW;
                     const uint32_t b_hi = b_base + s * Cfg::B_STAGE;
                     const uint32_t b_lo = b_hi + BN * 128;
                     const uint32_t acc = tmem + (uint32_t)((kb % NACC) * Cfg::ACC_COLS);
                     const uint32_t fresh = (kb < NACC) ? 0u : 1u;
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t dah = make_desc_sbo(a_hi0 + shift + kk * 32, kPitch * 128), dbh = make_desc(b_hi + kk * 32);
+                    for (int kk = 0; kk < Op::KSTEPS; ++kk) {
+                        const uint64_t dah = Op::desc(a_hi0 + shift + kk * 32, kPitch * Op::ROW), dbh = Op::desc(b_hi + kk * 32);
                         if (Cfg::CAT) {
                             const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kPitch * 128);
                             mma_tf32(acc, dah, dbh, idesc2, (kk ? 1u : fresh));       // [hi*hi | hi*lo]: B rows BN..2BN-1 are the lo image
@@ -268,7 +266,7 @@ __global__ void __launch_bounds__(kHaloThreads, 2) conv_halo_kernel(const __grid
                             mma_tf32(acc, dah, dbl, idesc, 1u);
                             mma_tf32(acc, dah, dbh, idesc, 1u);
                         } else {
-                            mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                            Op::mma(acc, dah, dbh, idesc, (kk ? 1u : fresh));
                         }
                     }
                     mma_commit(b_empty(s));
@@ -331,12 +329,12 @@ int conv_fwd_halo(const saunet_conv_desc* d, cudaStream_t st) {
     if (d->tc_bn == 128 && !SAUNET_ENV_FLAG("SAUNET_HALO_V1")) return conv_fwd_halo_persist(d, st);     // wide tiles: persistent kernel
     HaloP p; p.d = *d;
     p.tiles_x = d->Win / 8; p.tiles_y = d->Hin / 16; p.nchunk = d->Cin / 32; p.wt = d->w_tc;
-    const bool three = d->tc_passes != 1;
+    const int np = d->tc_passes;
     switch (d->tc_bn) {
-        case 16: return three ? launch_halo<16, 3>(p, st) : launch_halo<16, 1>(p, st);
-        case 32: return three ? launch_halo<32, 3>(p, st) : launch_halo<32, 1>(p, st);
-        case 64: return three ? launch_halo<64, 3>(p, st) : launch_halo<64, 1>(p, st);
-        case 128: return three ? launch_halo<128, 3>(p, st) : launch_halo<128, 1>(p, st);
+        case 16: return np == kBF16 ? launch_halo<16, kBF16>(p, st) : np != 1 ? launch_halo<16, 3>(p, st) : launch_halo<16, 1>(p, st);
+        case 32: return np == kBF16 ? launch_halo<32, kBF16>(p, st) : np != 1 ? launch_halo<32, 3>(p, st) : launch_halo<32, 1>(p, st);
+        case 64: return np == kBF16 ? launch_halo<64, kBF16>(p, st) : np != 1 ? launch_halo<64, 3>(p, st) : launch_halo<64, 1>(p, st);
+        case 128: return np == kBF16 ? launch_halo<128, kBF16>(p, st) : np != 1 ? launch_halo<128, 3>(p, st) : launch_halo<128, 1>(p, st);
     }
     set_error("conv2d_fwd(halo): unsupported N tile %d", d->tc_bn);
     return SAUNET_ERR_BAD_SHAPE;

@@ -40,10 +40,12 @@ constexpr int kPHaloIters = (kPHaloItems + kHaloPProducers - 1) / kHaloPProducer
 
 template <int BN, int NPASS>
 struct HaloPCfg {
-    static constexpr int NOP = (NPASS == 3) ? 2 : 1;
+    using Op = Opnd<NPASS>;
+    static constexpr int NOP = Op::NOP;
     static constexpr int NBUF = 2;                                   // patch buffers
-    static constexpr int PATCH = NOP * kPPatchBytes;                  // one buffer
-    static constexpr int B_STAGE = NOP * BN * 128;
+    static constexpr int IMG = Op::BF ? kPPatchBytes / 2 : kPPatchBytes;   // one patch image (bf16: 64-byte rows)
+    static constexpr int PATCH = NOP * IMG;                           // one buffer
+    static constexpr int B_STAGE = NOP * BN * Op::ROW;
     static constexpr int RED_BYTES = 8 * BN * 4;
     static constexpr int B_SPACE = 224 * 1024 - NBUF * PATCH - RED_BYTES;
     static constexpr int NSTB_RAW = B_SPACE / B_STAGE;
@@ -122,7 +124,7 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
             const int py = pix / 10, px = pix - py * 10;
             const int pr = py * kPPitch + px;
             p_rc[i] = it < kPHaloItems ? ((py << 8) | px) : -1;
-            s_off[i] = (uint32_t)pr * 128u + (uint32_t)((chunk ^ (pr & 7)) << 4);
+            s_off[i] = Opnd<NPASS>::off(pr, chunk);
         }
         int g_off[kPHaloIters];           // element offset of the halo pixel (channel chunk*4) in the load cursor's tile, -1 = outside
         int l_ti = -1, l_next_ti = 0, l_cc = 0;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
             }
             mbar_wait(patch_empty(buf), ph ^ 1u);
             uint8_t* hi_img = sgen + buf * Cfg::PATCH;
-            uint8_t* lo_img = hi_img + kPPatchBytes;
+            uint8_t* lo_img = hi_img + Cfg::IMG;
 #pragma unroll
             for (int i = 0; i < kPHaloIters; ++i) {
                 if (p_rc[i] < 0) continue;
@@ -168,12 +170,7 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
                     tv.x = fmaf(tv.x, sc.x, sh.x); tv.y = fmaf(tv.y, sc.y, sh.y); tv.z = fmaf(tv.z, sc.z, sh.z); tv.w = fmaf(tv.w, sc.w, sh.w);
                     if (d.in_relu) { tv.x = fmaxf(tv.x, 0.f); tv.y = fmaxf(tv.y, 0.f); tv.z = fmaxf(tv.z, 0.f); tv.w = fmaxf(tv.w, 0.f); }
                 }
-                float4 hi = split_hi4(tv);
-                *reinterpret_cast<float4*>(hi_img + s_off[i]) = hi;
-                if (NPASS == 3) {
-                    float4 lo = split_lo4(tv, hi);
-                    *reinterpret_cast<float4*>(lo_img + s_off[i]) = lo;
-                }
+                Opnd<NPASS>::store(hi_img, lo_img, s_off[i], tv);
             }
             fence_proxy_async();
             __syncwarp();
@@ -192,8 +189,9 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            using Op = Opnd<NPASS>;
+            const uint32_t idesc = Op::idesc(BN);
+            const uint32_t idesc2 = Op::idesc(2 * BN);
             int f = 0, g = 0;                     // flat patch / weight-stage counters
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int abuf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
@@ -204,20 +202,20 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
                     const int buf = f & 1; const uint32_t pph = (f >> 1) & 1;
                     mbar_wait(patch_full(buf), pph);
                     const uint32_t a_hi0 = sbase + buf * Cfg::PATCH;
-                    const uint32_t a_lo0 = a_hi0 + kPPatchBytes;
+                    const uint32_t a_lo0 = a_hi0 + Cfg::IMG;
                     for (int tap = 0; tap < 9; ++tap, ++kb, ++g) {
                         const int s = g % NSTB; const uint32_t ph = (g / NSTB) & 1;
                         mbar_wait(b_full(s), ph);
                         tc_fence_after();
                         const int ky = tap / 3, kx = tap - ky * 3;
-                        const uint32_t shift = (uint32_t)(ky * kPPitch + kx) * 128u;
+                        const uint32_t shift = (uint32_t)(ky * kPPitch + kx) * Op::ROW;
                         const uint32_t b_hi = b_base + s * Cfg::B_STAGE;
                         const uint32_t b_lo = b_hi + BN * 128;
                         const uint32_t acc = tmem + (uint32_t)(abuf * Cfg::BUF_COLS + (kb % NACC) * Cfg::ACC_COLS);
                         const uint32_t fresh = (kb < NACC) ? 0u : 1u;
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const uint64_t dah = make_desc_sbo(a_hi0 + shift + kk * 32, kPPitch * 128), dbh = make_desc(b_hi + kk * 32);
+                        for (int kk = 0; kk < Op::KSTEPS; ++kk) {
+                            const uint64_t dah = Op::desc(a_hi0 + shift + kk * 32, kPPitch * Op::ROW), dbh = Op::desc(b_hi + kk * 32);
                             if (Cfg::CAT) {
                                 const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kPPitch * 128);
                                 mma_tf32(acc, dah, dbh, idesc2, (kk ? 1u : fresh));       // [hi*hi | hi*lo]: B rows BN..2BN-1 are the lo image
@@ -228,7 +226,7 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
                                 mma_tf32(acc, dah, dbl, idesc, 1u);
                                 mma_tf32(acc, dah, dbh, idesc, 1u);
                             } else {
-                                mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                                Op::mma(acc, dah, dbh, idesc, (kk ? 1u : fresh));
                             }
                         }
                         mma_commit(b_empty(s));
@@ -372,6 +370,7 @@ static int launch_halo_persist(const HaloPP& p0, cudaStream_t st) {
 int conv_fwd_halo_persist(const saunet_conv_desc* d, cudaStream_t st) {
     HaloPP p; p.d = *d;
     p.tiles_x = d->Win / 8; p.tiles_y = d->Hin / 16; p.nchunk = d->Cin / 32; p.wt = d->w_tc;
+    if (d->tc_passes == kBF16) return launch_halo_persist<128, kBF16>(p, st);
     return d->tc_passes != 1 ? launch_halo_persist<128, 3>(p, st) : launch_halo_persist<128, 1>(p, st);
 }
 

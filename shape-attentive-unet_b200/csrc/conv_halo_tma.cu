@@ -40,13 +40,26 @@ constexpr int kTHaloIters = (kTHaloItems + kHaloTXform - 1) / kHaloTXform;   // 
 
 template <int BN, int NPASS>
 struct HaloTCfg {
-    static constexpr int NOP = (NPASS == 3) ? 2 : 1;
-    static constexpr int NBUF = BN >= 64 ? 2 : 3;                    // patch buffers (wide tiles need the room for weight stages)
-    static constexpr int PATCH = NOP * kTPatchBytes;                  // one buffer
-    static constexpr int B_TAP = NOP * BN * 128;                      // weight image of one (chunk, tap)
+    using Op = Opnd<NPASS>;
+    static constexpr int NOP = Op::NOP;
+    // patch buffers (tf32: wide tiles need the room for weight stages).  bf16: the MMAs of a chunk take ~600 clocks while a
+    // TMA box (180 separate 128-byte rows) takes several thousand to land -- ncu on 64 -> 64 at 256x256 with two buffers:
+    // 13 % tensor-active, 21 % DRAM, nothing saturated -- so four boxes are kept in flight
+#ifndef SAUNET_TMA_BF16_NBUF
+#define SAUNET_TMA_BF16_NBUF 4
+#endif
+    static constexpr int NBUF = Op::BF ? SAUNET_TMA_BF16_NBUF : (BN >= 64 ? 2 : 3);
+    // bf16 operands: the raw fp32 box is followed by the bf16 operand image (64-byte rows, SWIZZLE_64B) the transform warps
+    // write and the MMAs read; 12 KB keeps every buffer 1024-byte aligned (what the TMA swizzle needs)
+    static constexpr int BF_IMG = 12 * 1024;
+    static constexpr int PATCH = Op::BF ? kTPatchBytes + BF_IMG : NOP * kTPatchBytes;      // one buffer
+    static constexpr int B_TAP = NOP * BN * Op::ROW;                  // weight image of one (chunk, tap)
     // Narrow tiles issue only 8 short MMAs per tap: one barrier round trip per tap (~100 clocks of try_wait + commit on
     // the single issuing thread) would cost as much as the MMAs themselves, so a weight stage holds G consecutive taps.
-    static constexpr int G = BN <= 16 ? 9 : (BN <= 64 ? 3 : 1);
+#ifndef SAUNET_TMA_BF16_G
+#define SAUNET_TMA_BF16_G(bn) ((bn) <= 64 ? 9 : 3)
+#endif
+    static constexpr int G = Op::BF ? SAUNET_TMA_BF16_G(BN) : (BN <= 16 ? 9 : (BN <= 64 ? 3 : 1));   // (bf16: 2 MMAs per tap)
     static constexpr int B_STAGE = G * B_TAP;
     static constexpr int RED_BYTES = 8 * BN * 4;
     static constexpr int B_SPACE = 224 * 1024 - NBUF * PATCH - RED_BYTES;
@@ -136,6 +149,7 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
         // ================= transform warps: raw fp32 patch -> MMA operands, in place =================
         const int chunk = tid & 7;
         uint32_t s_off[kTHaloIters];      // byte offset inside a patch image (tile independent)
+        uint32_t b_off[kTHaloIters];      // bf16 operands: byte offset inside the bf16 image
         int p_rc[kTHaloIters];            // patch (row << 8 | col), -1: no such item
 #pragma unroll
         for (int i = 0; i < kTHaloIters; ++i) {
@@ -145,6 +159,7 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
             const int pr = py * kTPitch + px;
             p_rc[i] = it < kTHaloItems ? ((py << 8) | px) : -1;
             s_off[i] = (uint32_t)pr * 128u + (uint32_t)((chunk ^ (pr & 7)) << 4);
+            b_off[i] = Opnd<kBF16>::off(pr, chunk);
         }
         const bool pro = d.in_scale != nullptr;
         int f = 0;
@@ -170,7 +185,7 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                 uint8_t* hi_img = sgen + buf * Cfg::PATCH;
                 uint8_t* lo_img = hi_img + kTPatchBytes;
                 mbar_wait(raw_full(buf), ph);
-                if (pro || NPASS == 3) {
+                if (pro || NPASS == 3 || Opnd<NPASS>::BF) {
                     float4 v[kTHaloIters];
 #pragma unroll
                     for (int i = 0; i < kTHaloIters; ++i)
@@ -184,8 +199,9 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                                 tv.x = fmaf(tv.x, sc.x, sh.x); tv.y = fmaf(tv.y, sc.y, sh.y); tv.z = fmaf(tv.z, sc.z, sh.z); tv.w = fmaf(tv.w, sc.w, sh.w);
                                 if (d.in_relu) { tv.x = fmaxf(tv.x, 0.f); tv.y = fmaxf(tv.y, 0.f); tv.z = fmaxf(tv.z, 0.f); tv.w = fmaxf(tv.w, 0.f); }
                             }
-                            *reinterpret_cast<float4*>(hi_img + s_off[i]) = split_hi4(tv);
+                            if (!Opnd<NPASS>::BF) *reinterpret_cast<float4*>(hi_img + s_off[i]) = split_hi4(tv);
                         }
+                        if (Opnd<NPASS>::BF) { Opnd<kBF16>::store(lo_img, nullptr, b_off[i], tv); continue; }     // raw fp32 -> bf16 image
 #ifdef SAUNET_SPLIT_RN
                         else if (NPASS == 3) *reinterpret_cast<float4*>(hi_img + s_off[i]) = split_hi4(tv);
 #endif
@@ -199,8 +215,9 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            using Op = Opnd<NPASS>;
+            const uint32_t idesc = Op::idesc(BN);
+            const uint32_t idesc2 = Op::idesc(2 * BN);
             int f = 0, g = 0;                     // flat patch / weight-stage counters
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int abuf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
@@ -210,7 +227,8 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                 for (int cc = 0; cc < nchunk; ++cc, ++f) {
                     const int buf = f % NBUF; const uint32_t pph = (f / NBUF) & 1;
                     mbar_wait(patch_full(buf), pph);
-                    const int ksteps = (d.Cin - cc * 32) >= 32 ? 4 : (d.Cin - cc * 32 + 7) / 8;      // zero-padded K tail: skip it
+                    const int krem = d.Cin - cc * 32;                                                 // zero-padded K tail: skip it
+                    const int ksteps = krem >= 32 ? Op::KSTEPS : (Op::BF ? (krem + 15) / 16 : (krem + 7) / 8);
                     const uint32_t a_hi0 = sbase + buf * Cfg::PATCH;
                     const uint32_t a_lo0 = a_hi0 + kTPatchBytes;
                     for (int tg = 0; tg < 9 / Cfg::G; ++tg, ++g) {
@@ -221,7 +239,7 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                         for (int t = 0; t < Cfg::G; ++t, ++kb) {
                             const int tap = tg * Cfg::G + t;
                             const int ky = tap / 3, kx = tap - ky * 3;
-                            const uint32_t shift = (uint32_t)(ky * kTPitch + kx) * 128u;
+                            const uint32_t shift = (uint32_t)(ky * kTPitch + kx) * Op::ROW;
                             const uint32_t b_hi = b_base + s * Cfg::B_STAGE + t * Cfg::B_TAP;
                             const uint32_t b_lo = b_hi + BN * 128;
                             const uint32_t acc = tmem + (uint32_t)(abuf * Cfg::BUF_COLS + (kb % NACC) * Cfg::ACC_COLS);
@@ -229,6 +247,10 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
                                 if (kk >= ksteps) break;
+                                if (Op::BF) {          // the operand is the bf16 image behind the raw patch
+                                    Op::mma(acc, Op::desc(a_lo0 + shift + kk * 32, kTPitch * Op::ROW), Op::desc(b_hi + kk * 32), idesc, (kk ? 1u : fresh));
+                                    continue;
+                                }
                                 const uint64_t dah = make_desc_sbo(a_hi0 + shift + kk * 32, kTPitch * 128), dbh = make_desc(b_hi + kk * 32);
                                 if (Cfg::CAT) {
                                     const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kTPitch * 128);
@@ -434,6 +456,9 @@ bool conv_halo_tma_eligible(const saunet_conv_desc* d) {
     // register-gather kernel stays ahead while it has >= 2 waves of tiles per SM (114 vs 98 TFLOP/s at 128x128,
     // 128 -> 32); prologue-free operands (only lo written) and small problems (latency-bound: 64 vs 54 at 32x32) are faster
     // through TMA (64 -> 64 at 256x256: 194 vs 158 TFLOP/s).
+    // bf16 operands: the MMAs read a quarter of the bytes, the raw patch no longer competes with them for shared-memory
+    // bandwidth -> every eligible layer (SAUNET_BF16_HALO_LDG: apply the exclusions measured for tf32 operands)
+    if (d->tc_passes == kBF16 && !SAUNET_ENV_FLAG("SAUNET_BF16_HALO_LDG")) return true;
     const long long tiles = (long long)d->B * (d->Hin / 16) * (d->Win / 8);
     if (d->in_scale && d->tc_bn <= 64 && tiles >= 2 * 2 * kNumSMs) return false;
     if (!d->in_scale && d->tc_bn <= 64 && d->Cin >= 256) return false;
@@ -443,12 +468,12 @@ bool conv_halo_tma_eligible(const saunet_conv_desc* d) {
 int conv_fwd_halo_tma(const saunet_conv_desc* d, cudaStream_t st) {
     HaloTP p; p.d = *d;
     p.tiles_x = d->Win / 8; p.tiles_y = d->Hin / 16; p.nchunk = (d->Cin + 31) / 32; p.wt = d->w_tc;
-    const bool three = d->tc_passes != 1;
+    const int np = d->tc_passes;
     switch (d->tc_bn) {
-        case 16: return three ? launch_halo_tma<16, 3>(p, st) : launch_halo_tma<16, 1>(p, st);
-        case 32: return three ? launch_halo_tma<32, 3>(p, st) : launch_halo_tma<32, 1>(p, st);
-        case 64: return three ? launch_halo_tma<64, 3>(p, st) : launch_halo_tma<64, 1>(p, st);
-        case 128: return three ? launch_halo_tma<128, 3>(p, st) : launch_halo_tma<128, 1>(p, st);
+        case 16: return np == kBF16 ? launch_halo_tma<16, kBF16>(p, st) : np != 1 ? launch_halo_tma<16, 3>(p, st) : launch_halo_tma<16, 1>(p, st);
+        case 32: return np == kBF16 ? launch_halo_tma<32, kBF16>(p, st) : np != 1 ? launch_halo_tma<32, 3>(p, st) : launch_halo_tma<32, 1>(p, st);
+        case 64: return np == kBF16 ? launch_halo_tma<64, kBF16>(p, st) : np != 1 ? launch_halo_tma<64, 3>(p, st) : launch_halo_tma<64, 1>(p, st);
+        case 128: return np == kBF16 ? launch_halo_tma<128, kBF16>(p, st) : np != 1 ? launch_halo_tma<128, 3>(p, st) : launch_halo_tma<128, 1>(p, st);
     }
     set_error("conv2d_fwd(halo_tma): unsupported N tile %d", d->tc_bn);
     return SAUNET_ERR_BAD_SHAPE;

@@ -35,8 +35,9 @@ constexpr int kTProd = 512, kTEpi = 256, kTThreads = kTProd + kTEpi + 64;
 
 template <int NPASS>
 struct PwtCfg {
-    static constexpr int NOP = NPASS == 3 ? 2 : 1;
-    static constexpr int X_IMG = kTNP * 128, W_IMG = 128 * 128;
+    using Op = Opnd<NPASS>;
+    static constexpr int NOP = Op::NOP;
+    static constexpr int X_IMG = kTNP * Op::ROW, W_IMG = 128 * Op::ROW;
     static constexpr int STAGE = NOP * (X_IMG + W_IMG);
     static constexpr int NSTAGE = (200 * 1024) / STAGE > 4 ? 4 : (200 * 1024) / STAGE;       // 2 (3xTF32) or 4
     static constexpr int STG = 16 * 128 * 4;                   // fused BN-backward epilogue: 16 pixels x 128 channels staged per chunk
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
         const int chunk = tid & 7, rbase = tid >> 3;
         uint32_t s_off[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { const int r = rbase + 64 * i; s_off[i] = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4); }
+        for (int i = 0; i < 4; ++i) { const int r = rbase + 64 * i; s_off[i] = Opnd<NPASS>::off(r, chunk); }
         const int total = my_tiles * nkb;
         int l_ti = 0, l_kb = 0;
         // `tag`: channel of the thread's chunk (0xFFFFF: K padding) | one validity bit per row (pixels past M stay exactly zero)
@@ -118,12 +119,7 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
                     t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
                     if (d.in_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
                 }
-                const float4 hi = split_hi4(t);
-                *reinterpret_cast<float4*>(x_hi + s_off[i]) = hi;
-                if (NPASS == 3) {
-                    const float4 lo = split_lo4(t, hi);
-                    *reinterpret_cast<float4*>(x_lo + s_off[i]) = lo;
-                }
+                Opnd<NPASS>::store(x_hi, x_lo, s_off[i], t);
             }
             fence_proxy_async();
             __syncwarp();
@@ -139,8 +135,9 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
         }
     } else if (warp == MMA_WARP) {
         if (lane == 0) {
-            // D=f32, A=B=tf32, both K-major, N=256 (pixels), M=128 (channels)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTNP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // D=f32, A=B=tf32 (bf16), both K-major, N=256 (pixels), M=128 (channels)
+            using Op = Opnd<NPASS>;
+            const uint32_t idesc = Op::idesc(kTNP);
             int f = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int buf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
@@ -155,15 +152,15 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
                     const uint32_t w_hi = x_hi + Cfg::NOP * Cfg::X_IMG, w_lo = w_hi + Cfg::W_IMG;
                     const uint32_t acc = tmem + (uint32_t)(buf * kTNP);
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t dwh = make_desc(w_hi + kk * 32), dxh = make_desc(x_hi + kk * 32);
+                    for (int kk = 0; kk < Op::KSTEPS; ++kk) {
+                        const uint64_t dwh = Op::desc(w_hi + kk * 32), dxh = Op::desc(x_hi + kk * 32);
                         if (NPASS == 3) {
-                            const uint64_t dwl = make_desc(w_lo + kk * 32), dxl = make_desc(x_lo + kk * 32);
+                            const uint64_t dwl = Op::desc(w_lo + kk * 32), dxl = Op::desc(x_lo + kk * 32);
                             mma_tf32(acc, dwl, dxh, idesc, (kb | kk) ? 1u : 0u);
                             mma_tf32(acc, dwh, dxl, idesc, 1u);
                             mma_tf32(acc, dwh, dxh, idesc, 1u);
                         } else {
-                            mma_tf32(acc, dwh, dxh, idesc, (kb | kk) ? 1u : 0u);
+                            Op::mma(acc, dwh, dxh, idesc, (kb | kk) ? 1u : 0u);
                         }
                     }
                     mma_commit(empty(s));
@@ -343,7 +340,7 @@ int conv_fwd_pw_t(const saunet_conv_desc* d, cudaStream_t st) {
     p.ntile_co = cdiv(d->Cout, 128);
     p.ntiles = cdiv(p.M, kTNP) * p.ntile_co;
     p.wt = d->w_tc;
-    return d->tc_passes != 1 ? launch_pwt<3>(p, st) : launch_pwt<1>(p, st);
+    return d->tc_passes == kBF16 ? launch_pwt<kBF16>(p, st) : d->tc_passes != 1 ? launch_pwt<3>(p, st) : launch_pwt<1>(p, st);
 }
 
 }  // namespace saunet

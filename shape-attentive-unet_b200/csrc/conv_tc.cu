@@ -40,9 +40,10 @@ struct TcP {
 
 template <int BN, int NPASS>
 struct TcCfg {
-    static constexpr int A_BYTES = 128 * 128;
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int NOP = (NPASS == 3) ? 2 : 1;                 // hi (+ lo) images per operand
+    using Op = Opnd<NPASS>;
+    static constexpr int A_BYTES = 128 * Op::ROW;
+    static constexpr int B_BYTES = BN * Op::ROW;
+    static constexpr int NOP = Op::NOP;                              // hi (+ lo) images per operand (bf16: one image of 64-byte rows)
     static constexpr int STAGE = NOP * (A_BYTES + B_BYTES);
     static constexpr int RED_BYTES = 8 * BN * 4;                     // [4 lane quarters][sum, sumsq][BN] floats
     // output staging tile for the bulk-copy epilogue: 128 rows of BN floats at a pitch of BN*4 + 16 bytes (the 16 bytes
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             const int r = rbase + RSTEP * i;
-            s_off[i] = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+            s_off[i] = Opnd<NPASS>::off(r, chunk);
         }
         auto set_tile = [&](int ti) {
             const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -196,12 +197,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     t.x = fmaf(t.x, sc.x, sh.x); t.y = fmaf(t.y, sc.y, sh.y); t.z = fmaf(t.z, sc.z, sh.z); t.w = fmaf(t.w, sc.w, sh.w);
                     if (d.in_relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
                 }
-                float4 hi = split_hi4(t);
-                *reinterpret_cast<float4*>(a_hi + s_off[i]) = hi;
-                if (NPASS == 3) {
-                    float4 lo = split_lo4(t, hi);
-                    *reinterpret_cast<float4*>(a_lo + s_off[i]) = lo;
-                }
+                Opnd<NPASS>::store(a_hi, a_lo, s_off[i], t);
             }
             TC_PROF_ADD(pw_load);          // (first use of the gathered registers: global-load latency lands here)
             // every writer fences its own generic-proxy stores towards the async proxy, the warp converges, and ONE
@@ -229,8 +225,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=tf32, both K-major, N=BN, M=128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // instruction descriptor: D=f32, A=B=tf32 (bf16), both K-major, N=BN, M=128
+            using Op = Opnd<NPASS>;
+            const uint32_t idesc = Op::idesc(BN);
             long long mw_te = 0, mw_fa = 0, mw_fb = 0, mw_issue = 0;
             int f = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
@@ -253,15 +250,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     const uint32_t acc = tmem + (uint32_t)(buf * Cfg::BUF_COLS + (kb % NACC) * Cfg::ACC_COLS);
                     const uint32_t fresh = (kb < NACC) ? 0u : 1u;          // first k-block of each accumulator overwrites
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        const uint64_t dah = make_desc(a_hi + kk * 32), dbh = make_desc(b_hi + kk * 32);
+                    for (int kk = 0; kk < Op::KSTEPS; ++kk) {
+                        const uint64_t dah = Op::desc(a_hi + kk * 32), dbh = Op::desc(b_hi + kk * 32);
                         if (NPASS == 3) {
-                            const uint64_t dal = make_desc(a_lo + kk * 32), dbl = make_desc(b_lo + kk * 32);
+                            const uint64_t dal = Op::desc(a_lo + kk * 32), dbl = Op::desc(b_lo + kk * 32);
                             mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));       // small terms first
                             mma_tf32(acc, dah, dbl, idesc, 1u);
                             mma_tf32(acc, dah, dbh, idesc, 1u);
                         } else {
-                            mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                            Op::mma(acc, dah, dbh, idesc, (kk ? 1u : fresh));
                         }
                     }
                     mma_commit(empty(s));
@@ -452,6 +449,33 @@ __global__ void pack_tc_kernel(const float* __restrict__ kn, int K, int N, int B
     }
 }
 
+// bf16 image: [n_tile][k_block][BN][32 bf16] -- 64-byte rows in the K-major SWIZZLE_64B pattern (see Opnd<kBF16>)
+__global__ void pack_tc_bf16_kernel(const float* __restrict__ kn, int K, int N, int BN, int nkb, int taps, int Cin,
+                                    int chunk_major, uint16_t* __restrict__ out) {
+    const int ntile = (N + BN - 1) / BN;
+    const long long total = (long long)ntile * nkb * BN * 32;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        long long r = idx;
+        const int e = (int)(r % 8); r /= 8;           // element within the 16-byte chunk
+        const int pc = (int)(r % 4); r /= 4;          // physical chunk within the 64-byte row
+        const int row = (int)(r % BN); r /= BN;
+        const int kb = (int)(r % nkb); r /= nkb;
+        const int nt = (int)r;
+        const int lc = pc ^ ((row >> 1) & 3);         // logical chunk
+        int k = kb * 32 + lc * 8 + e;
+        bool kval = k < K;
+        if (chunk_major) {
+            const int cc = kb / taps, tap = kb - cc * taps, cch = cc * 32 + lc * 8 + e;
+            k = tap * Cin + cch; kval = cch < Cin;
+        }
+        const int n = nt * BN + row;
+        const float w = (kval && n < N) ? kn[(size_t)k * N + n] : 0.f;
+        uint32_t b;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b) : "f"(0.f), "f"(w));
+        out[idx] = (uint16_t)(b & 0xFFFFu);
+    }
+}
+
 template <int BN, int NPASS, int MODE>
 static int launch_tc_mode(const TcP& p, cudaStream_t st) {
     using Cfg = TcCfg<BN, NPASS>;
@@ -499,12 +523,12 @@ int conv_fwd_tc(const saunet_conv_desc* d, cudaStream_t st) {
     SAUNET_CHECK_ARG(M > 0 && M < (1ll << 31), SAUNET_ERR_BAD_SHAPE, "conv2d_fwd(tc): bad M=%lld", M);
     p.M = (int)M; p.K = d->KH * d->KW * d->Cin; p.HgWg = d->Hg * d->Wg; p.nkb = (p.K + 31) / 32; p.wt = d->w_tc;
     p.chunk_major = saunet_tc_chunk_major(d->KH * d->KW, d->Cin);
-    const bool three = d->tc_passes != 1;
+    const int np = d->tc_passes;
     switch (d->tc_bn) {
-        case 16: return three ? launch_tc<16, 3>(p, st) : launch_tc<16, 1>(p, st);
-        case 32: return three ? launch_tc<32, 3>(p, st) : launch_tc<32, 1>(p, st);
-        case 64: return three ? launch_tc<64, 3>(p, st) : launch_tc<64, 1>(p, st);
-        case 128: return three ? launch_tc<128, 3>(p, st) : launch_tc<128, 1>(p, st);
+        case 16: return np == kBF16 ? launch_tc<16, kBF16>(p, st) : np != 1 ? launch_tc<16, 3>(p, st) : launch_tc<16, 1>(p, st);
+        case 32: return np == kBF16 ? launch_tc<32, kBF16>(p, st) : np != 1 ? launch_tc<32, 3>(p, st) : launch_tc<32, 1>(p, st);
+        case 64: return np == kBF16 ? launch_tc<64, kBF16>(p, st) : np != 1 ? launch_tc<64, 3>(p, st) : launch_tc<64, 1>(p, st);
+        case 128: return np == kBF16 ? launch_tc<128, kBF16>(p, st) : np != 1 ? launch_tc<128, 3>(p, st) : launch_tc<128, 1>(p, st);
     }
     set_error("conv2d_fwd(tc): unsupported N tile %d", d->tc_bn);
     return SAUNET_ERR_BAD_SHAPE;
@@ -525,32 +549,39 @@ extern "C" int saunet_tc_tile_n(int Cout) {
 extern "C" long long saunet_tc_packed_floats_cm(int taps, int Cin, int N, int BN, int passes) {
     if (taps <= 0 || Cin <= 0 || N <= 0 || BN <= 0) return 0;
     const long long nkb = (long long)((Cin + 31) / 32) * taps, ntile = (N + BN - 1) / BN;
-    return ntile * nkb * (passes == 3 ? 2 : 1) * BN * 32;
+    return passes == kBF16 ? ntile * nkb * BN * 16 : ntile * nkb * (passes == 3 ? 2 : 1) * BN * 32;
 }
 extern "C" int saunet_pack_weights_tc_cm(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream) {
     SAUNET_CHECK_ARG(kn && out && taps > 0 && Cin > 0 && N > 0, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc_cm: bad args");
     SAUNET_CHECK_ARG(BN == 16 || BN == 32 || BN == 64 || BN == 128, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc_cm: bad N tile %d", BN);
-    SAUNET_CHECK_ARG(passes == 1 || passes == 3, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc_cm: passes must be 1 or 3");
-    const long long total = saunet_tc_packed_floats_cm(taps, Cin, N, BN, passes);
+    SAUNET_CHECK_ARG(passes == 1 || passes == 3 || passes == kBF16, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc_cm: passes must be 1, 3 or 16 (bf16)");
+    const long long total = saunet_tc_packed_floats_cm(taps, Cin, N, BN, passes) * (passes == kBF16 ? 2 : 1);
     int blocks = (int)((total + 255) / 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kn, taps * Cin, N, BN, passes, ((Cin + 31) / 32) * taps, taps, Cin, 1, out);
+    if (passes == kBF16)
+        pack_tc_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kn, taps * Cin, N, BN, ((Cin + 31) / 32) * taps, taps, Cin, 1, reinterpret_cast<uint16_t*>(out));
+    else
+        pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kn, taps * Cin, N, BN, passes, ((Cin + 31) / 32) * taps, taps, Cin, 1, out);
     SAUNET_CHECK_LAUNCH("pack_tc_kernel");
     return SAUNET_OK;
 }
 extern "C" long long saunet_tc_packed_floats(int K, int N, int BN, int passes) {
     if (K <= 0 || N <= 0 || BN <= 0) return 0;
     const long long nkb = (K + 31) / 32, ntile = (N + BN - 1) / BN;
-    return ntile * nkb * (passes == 3 ? 2 : 1) * BN * 32;
+    return passes == kBF16 ? ntile * nkb * BN * 16 : ntile * nkb * (passes == 3 ? 2 : 1) * BN * 32;      // (bf16: two elements per float)
 }
 extern "C" int saunet_pack_weights_tc(const float* kn, int taps, int Cin, int N, int BN, int passes, float* out, void* stream) {
     const int K = taps * Cin;
     SAUNET_CHECK_ARG(kn && out && taps > 0 && Cin > 0 && N > 0, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: bad args");
     SAUNET_CHECK_ARG(BN == 16 || BN == 32 || BN == 64 || BN == 128, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: bad N tile %d", BN);
-    SAUNET_CHECK_ARG(passes == 1 || passes == 3, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: passes must be 1 or 3");
-    const long long total = saunet_tc_packed_floats(K, N, BN, passes);
+    SAUNET_CHECK_ARG(passes == 1 || passes == 3 || passes == kBF16, SAUNET_ERR_BAD_SHAPE, "pack_weights_tc: passes must be 1, 3 or 16 (bf16)");
+    const long long total = saunet_tc_packed_floats(K, N, BN, passes) * (passes == kBF16 ? 2 : 1);
     int blocks = (int)((total + 255) / 256); if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kn, K, N, BN, passes, (K + 31) / 32, taps, Cin,
-                                                             saunet_tc_chunk_major(taps, Cin), out);
+    if (passes == kBF16)
+        pack_tc_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kn, K, N, BN, (K + 31) / 32, taps, Cin,
+                                                                      saunet_tc_chunk_major(taps, Cin), reinterpret_cast<uint16_t*>(out));
+    else
+        pack_tc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kn, K, N, BN, passes, (K + 31) / 32, taps, Cin,
+                                                                 saunet_tc_chunk_major(taps, Cin), out);
     SAUNET_CHECK_LAUNCH("pack_tc_kernel");
     return SAUNET_OK;
 }

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv_wgrad_halo_kernel(const __
     const saunet_wgrad_desc& d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int MMA_WARP = kWhProducers / 32;
+    const bool one = d.precision == 2;          // single-pass TF32: the lo images are neither written nor multiplied
     const int cb0 = blockIdx.y * Cfg::NT;                // first Q channel of this CTA's tile
     const int t_beg = blockIdx.x * p.tiles_per_cta;
     int t_end = t_beg + p.tiles_per_cta; if (t_end > p.ntiles) t_end = p.ntiles;
@@ -140,9 +141,8 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv_wgrad_halo_kernel(const __
         };
         auto split_store = [&](uint8_t* hi_img, uint8_t* lo_img, uint32_t off, const float4& v) {
             float4 hi = split_hi4(v);
-            float4 lo = split_lo4(v, hi);
             *reinterpret_cast<float4*>(hi_img + off) = hi;
-            *reinterpret_cast<float4*>(lo_img + off) = lo;
+            if (!one) *reinterpret_cast<float4*>(lo_img + off) = split_lo4(v, hi);
         };
         auto store_tile = [&](int it, const float4 (&va)[Cfg::A_ITEMS], const float4 (&vb)[Cfg::B_ITEMS]) {
             const int s = it % nstage; const uint32_t ph = (it / nstage) & 1;
@@ -233,9 +233,11 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv_wgrad_halo_kernel(const __
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
                         const uint64_t po = (uint64_t)(r * 1280 >> 4), qo = (uint64_t)(r * 1024 >> 4);
-                        mma_tf32(tacc, dpl0 + po, dqh0 + qo, idesc, (it | r) ? 1u : 0u);
-                        mma_tf32(tacc, dph0 + po, dql0 + qo, idesc, 1u);
-                        mma_tf32(tacc, dph0 + po, dqh0 + qo, idesc, 1u);
+                        if (!one) {
+                            mma_tf32(tacc, dpl0 + po, dqh0 + qo, idesc, (it | r) ? 1u : 0u);
+                            mma_tf32(tacc, dph0 + po, dql0 + qo, idesc, 1u);
+                        }
+                        mma_tf32(tacc, dph0 + po, dqh0 + qo, idesc, (one && !(it | r)) ? 0u : 1u);
                     }
                 }
                 mma_commit(empty(s));

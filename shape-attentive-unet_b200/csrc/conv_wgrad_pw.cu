@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) conv_wgrad_pw_kernel(const __gr
     const saunet_wgrad_desc& d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int MMA_WARP = kPwProducers / 32;
+    const bool one = d.precision == 2;          // single-pass TF32: the lo images are neither written nor multiplied
     const int ca0 = blockIdx.y * 128;                     // dY channel tile (M side)
     const int cb0 = blockIdx.z * p.cb_per_cta;            // Q channel tile (N side)
     int ncb = d.Cb - cb0; if (ncb > p.cb_per_cta) ncb = p.cb_per_cta;
@@ -118,9 +119,8 @@ __global__ void __launch_bounds__(kPwThreads, 1) conv_wgrad_pw_kernel(const __gr
         };
         auto split_store = [&](uint8_t* hi_img, uint8_t* lo_img, uint32_t off, const float4& v) {
             float4 hi = split_hi4(v);
-            float4 lo = split_lo4(v, hi);
             *reinterpret_cast<float4*>(hi_img + off) = hi;
-            *reinterpret_cast<float4*>(lo_img + off) = lo;
+            if (!one) *reinterpret_cast<float4*>(lo_img + off) = split_lo4(v, hi);
         };
         auto store_kb = [&](int kb, const float4 (&va)[Cfg::A_ITEMS], const float4 (&vb)[Cfg::B_ITEMS], unsigned mask) {
             const int s = kb % nstage; const uint32_t ph = (kb / nstage) & 1;
@@ -196,9 +196,11 @@ __global__ void __launch_bounds__(kPwThreads, 1) conv_wgrad_pw_kernel(const __gr
                     for (int j = 0; j < 2; ++j) {                    // two 8-pixel K steps
                         const uint64_t dah = dT | (uint64_t)((a_hi + j * 1024) >> 4), dal = dT | (uint64_t)((a_hi + Cfg::A_IMG + j * 1024) >> 4);
                         const uint64_t dbh = dT | (uint64_t)((bq + j * 1024) >> 4), dbl = dT | (uint64_t)((bq + Cfg::B_IMG + j * 1024) >> 4);
-                        mma_tf32(tmem + (uint32_t)n0, dal, dbh, idesc, (kb | j) ? 1u : 0u);
-                        mma_tf32(tmem + (uint32_t)n0, dah, dbl, idesc, 1u);
-                        mma_tf32(tmem + (uint32_t)n0, dah, dbh, idesc, 1u);
+                        if (!one) {
+                            mma_tf32(tmem + (uint32_t)n0, dal, dbh, idesc, (kb | j) ? 1u : 0u);
+                            mma_tf32(tmem + (uint32_t)n0, dah, dbl, idesc, 1u);
+                        }
+                        mma_tf32(tmem + (uint32_t)n0, dah, dbh, idesc, (one && !(kb | j)) ? 0u : 1u);
                     }
                 }
                 mma_commit(empty(s));

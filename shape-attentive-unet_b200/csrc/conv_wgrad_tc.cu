@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
     const saunet_wgrad_desc& d = p.d;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int MMA_WARP = kWgProducers / 32;
+    const bool one = d.precision == 2;          // single-pass TF32: the lo images are neither written nor multiplied
 
     // tile decode.  The gathered operand Q is addressed by kq = tap*Cb + cb (im2col column), so a 128-wide tile
     // spans several taps when Cb is small and dY (P) is read once per tile, not once per tap.
@@ -170,9 +171,8 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
                     if (d.q_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
                 }
                 float4 hi = split_hi4(v);
-                float4 lo = split_lo4(v, hi);
                 *reinterpret_cast<float4*>(hi_img + off) = hi;
-                *reinterpret_cast<float4*>(lo_img + off) = lo;
+                if (!one) *reinterpret_cast<float4*>(lo_img + off) = split_lo4(v, hi);
             };
             auto load_block = [&](int kb, float4 (&vr)[RIT], float4 (&vs)[SIT]) {
                 if (kb >= nkb) return;
@@ -261,9 +261,11 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
                 for (int j = 0; j < 4; ++j) {                 // 4 groups of 8 pixels
                     const uint64_t drh = make_desc_mn(r_hi + j * 4096, 512, 2048), drl = make_desc_mn(r_lo + j * 4096, 512, 2048);
                     const uint64_t dsh = make_desc_mn(s_hi + j * (BN * 32), 512, BN * 16), dsl = make_desc_mn(s_lo + j * (BN * 32), 512, BN * 16);
-                    mma_tf32(acc, drl, dsh, idesc, (j ? 1u : fresh));
-                    mma_tf32(acc, drh, dsl, idesc, 1u);
-                    mma_tf32(acc, drh, dsh, idesc, 1u);
+                    if (!one) {
+                        mma_tf32(acc, drl, dsh, idesc, (j ? 1u : fresh));
+                        mma_tf32(acc, drh, dsl, idesc, 1u);
+                    }
+                    mma_tf32(acc, drh, dsh, idesc, one ? (j ? 1u : fresh) : 1u);
                 }
                 mma_commit(empty(s));
             }
@@ -293,7 +295,7 @@ static int launch_wg(const WgTcP& p, dim3 grid, cudaStream_t st) {
 }
 
 bool conv_wgrad_tc_eligible(const saunet_wgrad_desc* d) {
-    if (d->precision != 1) return false;
+    if (d->precision != 1 && d->precision != 2) return false;
     if (d->Ca % 4 || d->Cb % 4 || d->p_ld % 4 || d->q_ld % 4 || !aligned16(d->p) || !aligned16(d->q)) return false;
     if (d->q_scale && (!aligned16(d->q_scale) || !aligned16(d->q_shift))) return false;
     if (d->Ca < 8 || d->Cb < 4 || d->KH * d->KW * d->Cb < 32) return false;     // (Cb = 4: the channel-padded 7x7 stem)

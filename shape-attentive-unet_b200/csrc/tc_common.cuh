@@ -110,6 +110,66 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
+// ---- operand classes of the K-major kernels ----------------------------------------------------------------------------
+// NPASS = 3: 3xTF32 (hi + lo images, 128-byte rows of 32 fp32 channels, SWIZZLE_128B), NPASS = 1: single-pass TF32 (hi image
+// only), NPASS = kBF16: bf16 operands (kind::f16, fp32 accumulate) -- the same 32-channel chunk is a 64-byte row in the
+// K-major SWIZZLE_64B pattern (16-byte chunk index ^= absolute address bits [7,9)), two K = 16 MMAs per chunk.  Like the
+// 128-byte pattern it is a function of the absolute shared-memory address: a descriptor may start at any 64-byte row of a
+// halo patch and the stride between 8-row groups may be any multiple of 64 (tools/exp/umma_bf16_sw64_test.cu, B200).
+constexpr int kBF16 = 16;
+
+template <int NPASS>
+struct Opnd {
+    static constexpr bool BF = NPASS == kBF16;
+    static constexpr int ROW = BF ? 64 : 128;           // bytes per 32-channel operand row
+    static constexpr int NOP = NPASS == 3 ? 2 : 1;      // images per operand
+    static constexpr int KSTEPS = BF ? 2 : 4;           // MMAs (32 bytes of K each) per 32-channel chunk
+    // byte offset, inside an image whose base is 1024-byte aligned, of the 4-channel piece `chunk` (0..7) of row r
+    __device__ static __forceinline__ uint32_t off(int r, int chunk) {
+        if (BF) return (uint32_t)r * 64u + (uint32_t)((((chunk >> 1) ^ ((r >> 1) & 3)) << 4) | ((chunk & 1) << 3));
+        return (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+    }
+    // store 4 channels of one row into the operand image(s)
+    __device__ static __forceinline__ void store(uint8_t* hi_img, uint8_t* lo_img, uint32_t o, const float4& t) {
+        if (BF) {
+            uint32_t a, b;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(a) : "f"(t.y), "f"(t.x));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(b) : "f"(t.w), "f"(t.z));
+            *reinterpret_cast<uint2*>(hi_img + o) = make_uint2(a, b);
+        } else {
+            const float4 hi = split_hi4(t);
+            *reinterpret_cast<float4*>(hi_img + o) = hi;
+            if (NPASS == 3) *reinterpret_cast<float4*>(lo_img + o) = split_lo4(t, hi);
+        }
+    }
+    // shared-memory matrix descriptor (K-major), `sbo` = bytes between 8-row groups
+    __device__ static __forceinline__ uint64_t desc(uint32_t saddr, uint32_t sbo = 8 * ROW) {
+        uint64_t d = 0;
+        d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+        d |= (uint64_t)1 << 16;
+        d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+        d |= (uint64_t)1 << 46;
+        d |= (uint64_t)(BF ? 4 : 2) << 61;               // SWIZZLE_64B : SWIZZLE_128B
+        return d;
+    }
+    // instruction descriptor: D = f32, A = B = tf32 | bf16, both K-major, M = 128
+    __device__ static __forceinline__ uint32_t idesc(int n) {
+        const uint32_t fmt = BF ? 1u : 2u;
+        return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    }
+    __device__ static __forceinline__ void mma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t id, uint32_t acc) {
+        if (BF) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(id), "r"(acc) : "memory");
+        } else {
+            mma_tf32(tmem_c, adesc, bdesc, id, acc);
+        }
+    }
+};
+
 // epilogue math on one 16-column chunk of a row: v = acc + bias (exactly 0 for rows / columns outside the problem, so
 // that the BatchNorm statistics see nothing), o = act(v * rs).  Every branch is warp-uniform except the row mask.
 __device__ __forceinline__ void epi_chunk(float (&v)[16], float (&o)[16], const float* bias, int nvalid, bool tile_full,

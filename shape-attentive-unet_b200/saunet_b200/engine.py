@@ -412,14 +412,18 @@ def packed(tp, w, mode, A=None, Bc=None):
 #   "fp32"   exact fp32 FFMA implicit GEMM (conv_simt.cu)
 #   "3xtf32" tcgen05 tensor cores, hi/lo tf32 split of both operands, fp32 accumulate in TMEM (fp32-class accuracy)
 #   "tf32"   tcgen05, single pass (what cuDNN does by default for PyTorch convs); ~1e-3 relative error
+#   "bf16"   tcgen05 kind::f16 with bf16 operands and fp32 accumulation for every forward / data-gradient convolution
+#            (activations, BatchNorm statistics, loss, master weights and gradients stay fp32 in memory; operands are rounded
+#            to bf16 on their way into shared memory, weights are pre-tiled as bf16 images); weight gradients run
+#            single-pass TF32 (their MN-major operand layouts exist for 32-bit elements only) -- BASELINE configs[2]
 _PRECISION = os.environ.get("SAUNET_PRECISION", "3xtf32")
 _WIDE_TILES = os.environ.get("SAUNET_WIDE_TILES", "1") == "1"
 
 
 def set_precision(name):
     global _PRECISION
-    if name not in ("fp32", "3xtf32", "tf32"):
-        raise ValueError("precision must be fp32 | 3xtf32 | tf32")
+    if name not in ("fp32", "3xtf32", "tf32", "bf16"):
+        raise ValueError("precision must be fp32 | 3xtf32 | tf32 | bf16")
     _PRECISION = name
 
 
@@ -432,7 +436,7 @@ def packed_tc(tp, w, mode, taps, Cin, N, phase=0, M=None, cm=False, wide=False):
     M (GEMM rows) lets small problems take a narrower N tile so that at least ~one CTA per SM exists."""
     if _PRECISION == "fp32":
         return None
-    passes = 3 if _PRECISION == "3xtf32" else 1
+    passes = {"3xtf32": 3, "tf32": 1, "bf16": 16}[_PRECISION]
     lib = _C.load()
     bn = lib.saunet_tc_tile_n(N)
     if wide:
@@ -518,7 +522,7 @@ def wgrad(tp, p, q, dwptr, KH, KW, Hg, Wg, sy=1, sx=1, offy=0, offx=0, pro=0, pr
     else:
         d.q_scale, d.q_shift, d.q_relu = None, None, 0
     d.dw = dwptr
-    d.precision = 0 if _PRECISION == "fp32" else 1
+    d.precision = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16": 2}[_PRECISION]
     M = q.B * Hg * Wg
     _C.call("saunet_conv2d_wgrad", ctypes.byref(d), tp.stream, flops=2.0 * M * KH * KW * p.C * q.C,
             nbytes=4.0 * M * (p.C + q.C), tag="M%d taps%d Ca%d Cb%d s%d" % (M, KH * KW, p.C, q.C, sy))
