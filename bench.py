@@ -168,7 +168,9 @@ def run_ours(args):
         return loss
 
     def step_e2e():
-        if graphed is not None and use_graph:
+        if e2e_mode == "pipelined":
+            return loop.step(hb)
+        if graphed is not None and e2e_mode == "cuda_graph":
             loss = graphed(hb)
             arena.all_reduce()
             if opt is not None:
@@ -177,7 +179,7 @@ def run_ours(args):
         feed = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
         return float(step(feed).item())
 
-    def timed(fn, iters):
+    def timed(fn, iters, finish=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -185,6 +187,8 @@ def run_ours(args):
         e0.record()
         for _ in range(iters):
             fn()
+        if finish is not None:
+            finish()
         e1.record()
         if world > 1:
             dist.barrier()
@@ -294,23 +298,28 @@ def run_ours(args):
     ctx = None
     if args.torch_gpu_context and rank == 0:
         ctx = torch_gpu_context(dev, B)
-    # both launch modes are part of the public API (the eager call and its CUDA-graph replay): the end-to-end arm uses
-    # whichever is faster on this box -- the graph removes host launch time, the eager path keeps more kernels of
-    # different streams in flight (weight gradients beside data gradients); 3 untimed-then-3 timed steps each decide
-    use_graph = graphed is not None
-    if graphed is not None:
-        trial = {}
-        for mode in (True, False):
-            use_graph = mode
-            step_e2e()
-            trial[mode] = timed(step_e2e, 3)
-        use_graph = trial[True] <= trial[False]
-        if world > 1:                                   # every rank must take the same path
-            t = torch.tensor([1 if use_graph else 0], device=dev)
-            dist.broadcast(t, 0)
-            use_graph = bool(int(t.item()))
+    # three ways to drive the same step, all part of the public API: the plain eager call (copy, step, loss.item()), its
+    # CUDA-graph replay (saunet_b200.graphs.GraphedStep: no host launch time, but fewer kernels of different streams in
+    # flight) and the pipelined loop (saunet_b200.loop.TrainLoop: the next batch is copied on a copy stream while the
+    # current step computes, and a step's loss is read after the NEXT step has been issued).  Every mode copies every
+    # step's inputs from pinned host memory and reads every step's loss inside the timed region; the end-to-end arm uses
+    # whichever is fastest on this box (1 untimed + 3 timed steps each decide).
+    from saunet_b200.loop import TrainLoop
+    loop = TrainLoop(seg_mod, arena, hb, optimizer=opt)
+    modes = ["pipelined", "eager"] + (["cuda_graph"] if graphed is not None else [])
+    if args.e2e_mode != "auto":
+        modes = [args.e2e_mode]
+    trial = {}
+    for e2e_mode in modes:
+        step_e2e()
+        trial[e2e_mode] = timed(step_e2e, 3, finish=loop.flush if e2e_mode == "pipelined" else None)
+    e2e_mode = min(trial, key=trial.get)
+    if world > 1:                                       # every rank must take the same path
+        t = torch.tensor([modes.index(e2e_mode)], device=dev)
+        dist.broadcast(t, 0)
+        e2e_mode = modes[int(t.item())]
     step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, args.steps, finish=loop.flush if e2e_mode == "pipelined" else None)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     if rank == 0:
         h2d = sum(v.numel() * v.element_size() for v in hb.values())
@@ -322,7 +331,7 @@ def run_ours(args):
                                          dtype=args.dtype),
                "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                        "ms_per_step": round(ms_e2e / args.steps, 3),
-                       "launch": "cuda_graph" if (graphed is not None and use_graph) else "eager"},
+                       "launch": e2e_mode, "trial_ms_per_step": {k: round(v / 3, 3) for k, v in trial.items()}},
                "gpu_launches": int(launches), "clocks": clocks,
                "tensor_pipe_fraction": round(FLOP_PER_SLICE * value / world / (peaks()["tflops"] * 1e12), 4),
                "roofline": roof, "cpu_baseline": cpu_base}
@@ -449,7 +458,8 @@ def run_blocks(args):
     isolation by summing the CUDA-event times of its own C-ABI calls (saunet_b200._C.SCOPE == 'tail')."""
     from models.attention_blocks import DualAttBlock
     from models.GSConv import GatedSpatialConv2d
-    from saunet_b200 import _C
+    from saunet_b200 import _C, engine
+    engine.set_precision("bf16" if args.dtype == "bf16" else "3xtf32")
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     pk = peaks()
@@ -512,8 +522,9 @@ def run_blocks(args):
     best = max(r["tail_fwd_gbs"] for r in res["dualatt"])
     out = {"metric": "achieved HBM GB/s of algorithmic bytes, DualAttBlock attention tail / GatedSpatialConv2d, 128x128 maps, batch 32 "
                      "(BASELINE configs[3]); value = best attention-tail forward", "value": best, "unit": "GB/s", "n_gpus": 1,
-           "steps": args.steps, "warmup": 3, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "DualAttBlock([C,C]->C) and GatedSpatialConv2d(C,C), C in 64..512, 128x128 output, batch 32, train mode"},
+           "steps": args.steps, "warmup": 3, "higher_is_better": True, "dtype": args.dtype, "data": "synthetic",
+           "config": {"workload": "DualAttBlock([C,C]->C) and GatedSpatialConv2d(C,C), C in 64..512, 128x128 output, batch 32, train mode; "
+                                  + ARITH[args.dtype]},
            "peak": pk["hbm_gbs"], "peak_src": pk["src"], "results": res}
     print(json.dumps(out), flush=True)
 
@@ -525,6 +536,8 @@ def run_volume(args):
     from models import SAUNet
     from saunet_b200 import synth
     from saunet_b200.inference import predict_volume
+    from saunet_b200 import engine
+    engine.set_precision("bf16" if args.dtype == "bf16" else "3xtf32")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -551,8 +564,8 @@ def run_volume(args):
     if rank == 0:
         out = {"metric": "2D slices/sec, SAUNet volume inference (eval-mode BN, argmax on device, z axis sharded over ranks)",
                "value": res["8_volumes"]["slices_per_s"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": 3,
-               "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "16-slice 256x256x3 stacks, one and eight volumes per call (BASELINE configs[4])",
+               "higher_is_better": True, "scaling": "strong", "dtype": args.dtype, "data": "synthetic",
+               "config": {"workload": "16-slice 256x256x3 stacks, one and eight volumes per call (BASELINE configs[4]); " + ARITH[args.dtype],
                           "parallelism": "z-shard x%d" % world}, "results": res}
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -570,6 +583,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the e2e arm eagerly instead of through a CUDA graph")
+    ap.add_argument("--e2e-mode", default="auto", choices=["auto", "pipelined", "eager", "cuda_graph"])
     ap.add_argument("--workload", default="train", choices=["train", "train_loop", "blocks", "volume"])
     ap.add_argument("--optimizer", default="radam", choices=["radam", "sgd", "adam"], help="train_loop: fused optimizer (train.sh uses radam)")
     ap.add_argument("--torch-gpu-context", action="store_true",

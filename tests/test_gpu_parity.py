@@ -852,3 +852,41 @@ def test_graphed_step_matches_eager():
         n = unet.final.weight.numel()
         assert rel_err(arena.flat[o:o + n].cpu(), ge[o:o + n].cpu()) < 1e-3
         assert float((arena.flat - ge).norm() / ge.norm()) < 5e-2
+
+
+def test_train_loop_pipelined_matches_plain_steps():
+    """saunet_b200.loop.TrainLoop (next batch copied on a copy stream while the current step computes, loss read one step
+    late) returns, one call later, exactly the losses of the plain copy -> step -> item() loop, and steps the optimizer the
+    same way (fused SGD: the weights after 4 steps agree)."""
+    from models import SegmentationModule
+    from loss import DualLoss
+    from saunet_b200.loop import TrainLoop
+    from saunet_b200.optim import create_fused_optimizer
+    from saunet_b200.parallel import GradArena
+    feeds = [{k: v.pin_memory() for k, v in synth.synthetic_batch(2, 64, seed=s).items()} for s in (304, 7, 11, 304)]
+
+    def build():
+        unet = _model(True)
+        seg_mod = SegmentationModule(DualLoss(), unet, 4).to(DEV).train()
+        arena = GradArena(unet)
+        return unet, seg_mod, arena, create_fused_optimizer(unet, arena, "sgd", lr=1e-3)
+
+    unet, seg_mod, arena, opt = build()
+    plain = []
+    for f in feeds:
+        d = {k: v.to(DEV) for k, v in f.items()}
+        arena.zero()
+        loss, _ = seg_mod({"image": d["image"], "mask": (d["seg"], d["edge"])}, 0)
+        loss.backward()
+        arena.all_reduce()
+        opt.step()
+        plain.append(float(loss))
+    w_plain = unet.final.weight.detach().clone()
+    unet, seg_mod, arena, opt = build()
+    loop = TrainLoop(seg_mod, arena, feeds[0], optimizer=opt)
+    got = [loop.step(f) for f in feeds]
+    got = got[1:] + [loop.flush()]
+    assert loop.n == 4 and len(got) == 4
+    for a, b in zip(got, plain):
+        assert abs(a - b) < 2e-5 * abs(b), (got, plain)      # (atomics order differs run to run: not bitwise)
+    assert rel_err(unet.final.weight.detach().cpu(), w_plain.cpu()) < 1e-4
