@@ -295,6 +295,11 @@ def run_ours(args):
             print("CUDA-graph capture unavailable, e2e runs eagerly: %r" % (e,), file=sys.stderr)
             graphed = None
 
+    if world > 1:               # the graph mode is offered only if EVERY rank captured (the ranks must agree on the path)
+        t = torch.tensor([1 if graphed is not None else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0:
+            graphed = None
     ctx = None
     if args.torch_gpu_context and rank == 0:
         ctx = torch_gpu_context(dev, B)

@@ -25,7 +25,9 @@ class GraphedStep:
         dev = self.static["image"].device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):                     # warm-up on the side stream (lazy inits, allocator pools)
+        # (no collectives in the warm-up or the capture: the gradient all-reduce follows each replay -- arena.all_reduce();
+        #  an async all-reduce left in flight here would be joined from inside the capture and invalidate it)
+        with torch.cuda.stream(side), arena.no_sync():    # warm-up on the side stream (lazy inits, allocator pools)
             for _ in range(warmup):
                 self._eager(epoch, False)
         if optimizer is not None:
@@ -35,7 +37,7 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         engine.FORCE_PACK = True
         try:
-            with torch.cuda.graph(self.graph):
+            with arena.no_sync(), torch.cuda.graph(self.graph):
                 self.loss, self.acc = self._eager(epoch)
         finally:
             engine.FORCE_PACK = False

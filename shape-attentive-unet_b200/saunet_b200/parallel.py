@@ -86,7 +86,7 @@ class GradArena:
                     ents.append((first, self.packed_off[id(p)] - self.n_grad, self.offsets[id(p)], a_, b_, kh * kw))
                     first += p.numel()
             self._bucket_tables.append((self._make_table(ents, dev) if ents else None, len(ents), first))
-        self._schedule = None          # (n_ops, {op index -> [bucket, ...]}) learnt from the first backward
+        self._schedule = {}            # n_ops -> {op index -> [bucket, ...]}, learnt from the first backward of each tape length
         self._comm = None              # side stream for unpack + all-reduce
         self._works = []
         self._overlapped = False
@@ -109,10 +109,13 @@ class GradArena:
         for b, (_, _, ps) in enumerate(self.bucket_params):
             k = max([last_touch.get(id(p), -1) for p in ps] + [-1])
             sched.setdefault(max(k, 0), []).append(b)
-        self._schedule = (n_ops, sched)
+        # one schedule PER tape length: a differently shaped pass (e.g. the serialised profiling pass only rank 0 runs) must
+        # not evict the schedule of the regular step -- the ranks would then disagree on whether a backward overlaps its
+        # collectives, i.e. on the ORDER of the collectives
+        self._schedule[n_ops] = sched
 
     def schedule_for(self, n_ops):
-        return self._schedule[1] if self._schedule is not None and self._schedule[0] == n_ops else None
+        return self._schedule.get(n_ops)
 
     def _world(self, group=None):
         return dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
