@@ -37,6 +37,8 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+import datetime  # noqa: E402
+
 import torch  # noqa: E402
 
 METRIC = "2D slices/sec, SAUNet fwd+bwd 256x256x1->4-class (whole job, device-timed, max over ranks)"
@@ -122,7 +124,7 @@ def build_ours(dev, batch):
     unet.load_state_dict(synth.synthetic_state_dict(unet.state_dict(), seed=0))
     unet = unet.to(dev).train()
     seg_mod = SegmentationModule(DualLoss(num_classes=4), unet, 4).to(dev).train()
-    arena = GradArena(unet)
+    arena = GradArena(unet, bucket_mb=float(os.environ.get("SAUNET_BUCKET_MB", "32")))
     return seg_mod, unet, arena
 
 
@@ -142,7 +144,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # (a collective that cannot complete must fail the run within minutes, not hang it until the driver's clock runs out)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _C.load()
@@ -548,7 +551,8 @@ def run_volume(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # (a collective that cannot complete must fail the run within minutes, not hang it until the driver's clock runs out)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     with warnings.catch_warnings():

@@ -110,6 +110,23 @@ def test_grad_arena_packed_table_layout():
     assert float(arena.flat.abs().sum()) == 0.0 and float(arena.packed.min()) == 1.0     # zero() leaves the (self-clearing) images alone
 
 
+def test_grad_arena_keeps_one_bucket_schedule_per_tape_length():
+    """The overlap schedule (which backward op finalises which gradient bucket) is learnt per tape length.  A differently
+    shaped pass that only ONE rank runs (bench.py's serialised profiling pass on rank 0) must not evict the regular step's
+    schedule: that rank would fall back to a learning pass without overlapped collectives while the others issue theirs
+    from inside backward -- the ranks then disagree on the order of the all-reduces and the job deadlocks (seen on 2 GPUs)."""
+    from saunet_b200.parallel import GradArena
+    m = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Conv2d(8, 5, 1))
+    arena = GradArena(m, bucket_mb=0.0001)
+    assert len(arena.buckets) >= 2
+    ps = list(m.parameters())
+    arena.learn_schedule(10, {id(p): i for i, p in enumerate(ps)})
+    first = arena.schedule_for(10)
+    assert first is not None and sorted(b for bs in first.values() for b in bs) == list(range(len(arena.buckets)))
+    arena.learn_schedule(7, {id(p): 0 for p in ps})           # another tape length (e.g. concurrency switched off)
+    assert arena.schedule_for(10) == first and arena.schedule_for(7) is not None and arena.schedule_for(8) is None
+
+
 class _DataSGD(torch.optim.Optimizer):
     """writes through p.data like the reference's radam.py:76 (no version bump)"""
 
