@@ -188,40 +188,41 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
             }
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
-            using Op = Opnd<NPASS>;
-            const uint32_t idesc = Op::idesc(BN);
-            const uint32_t idesc2 = Op::idesc(2 * BN);
-            int f = 0, g = 0;                     // flat patch / weight-stage counters
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int abuf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
-                mbar_wait(tmem_empty(abuf), tph ^ 1u);
-                tc_fence_after();
-                int kb = 0;
-                for (int cc = 0; cc < nchunk; ++cc, ++f) {
-                    const int buf = f & 1; const uint32_t pph = (f >> 1) & 1;
-                    mbar_wait(patch_full(buf), pph);
-                    const uint32_t a_hi0 = sbase + buf * Cfg::PATCH;
-                    const uint32_t a_lo0 = a_hi0 + Cfg::IMG;
-                    for (int tap = 0; tap < 9; ++tap, ++kb, ++g) {
-                        const int s = g % NSTB; const uint32_t ph = (g / NSTB) & 1;
-                        mbar_wait(b_full(s), ph);
-                        tc_fence_after();
+        // converged warp, one elected lane issues; descriptors = templates advanced by adds (see conv_halo_tma.cu)
+        using Op = Opnd<NPASS>;
+        const uint32_t idesc = Op::idesc(BN);
+        const uint32_t idesc2 = Op::idesc(2 * BN);
+        const uint64_t a_tmpl = Op::desc(0, kPPitch * Op::ROW), b_tmpl = Op::desc(0);
+        const bool leader = elect_one();
+        int f = 0, g = 0;                     // flat patch / weight-stage counters
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int abuf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
+            mbar_wait(tmem_empty(abuf), tph ^ 1u);
+            tc_fence_after();
+            int kb = 0;
+            for (int cc = 0; cc < nchunk; ++cc, ++f) {
+                const int buf = f & 1; const uint32_t pph = (f >> 1) & 1;
+                mbar_wait(patch_full(buf), pph);
+                const uint64_t a_hi_d = a_tmpl + (uint64_t)((sbase + buf * Cfg::PATCH) >> 4), a_lo_d = a_hi_d + (uint64_t)(Cfg::IMG >> 4);
+                for (int tap = 0; tap < 9; ++tap, ++kb, ++g) {
+                    const int s = g % NSTB; const uint32_t ph = (g / NSTB) & 1;
+                    mbar_wait(b_full(s), ph);
+                    tc_fence_after();
+                    if (leader) {
                         const int ky = tap / 3, kx = tap - ky * 3;
-                        const uint32_t shift = (uint32_t)(ky * kPPitch + kx) * Op::ROW;
-                        const uint32_t b_hi = b_base + s * Cfg::B_STAGE;
-                        const uint32_t b_lo = b_hi + BN * 128;
+                        const uint64_t shift = (uint64_t)(((ky * kPPitch + kx) * Op::ROW) >> 4);
+                        const uint64_t b_hi_d = b_tmpl + (uint64_t)((b_base + s * Cfg::B_STAGE) >> 4), b_lo_d = b_hi_d + (uint64_t)((BN * 128) >> 4);
                         const uint32_t acc = tmem + (uint32_t)(abuf * Cfg::BUF_COLS + (kb % NACC) * Cfg::ACC_COLS);
                         const uint32_t fresh = (kb < NACC) ? 0u : 1u;
 #pragma unroll
                         for (int kk = 0; kk < Op::KSTEPS; ++kk) {
-                            const uint64_t dah = Op::desc(a_hi0 + shift + kk * 32, kPPitch * Op::ROW), dbh = Op::desc(b_hi + kk * 32);
+                            const uint64_t dah = a_hi_d + shift + (uint64_t)(kk * 2), dbh = b_hi_d + (uint64_t)(kk * 2);
                             if (Cfg::CAT) {
-                                const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kPPitch * 128);
+                                const uint64_t dal = a_lo_d + shift + (uint64_t)(kk * 2);
                                 mma_tf32(acc, dah, dbh, idesc2, (kk ? 1u : fresh));       // [hi*hi | hi*lo]: B rows BN..2BN-1 are the lo image
                                 mma_tf32(acc + BN, dal, dbh, idesc, 1u);                  // lo*hi joins the small-terms half
                             } else if (NPASS == 3) {
-                                const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kPPitch * 128), dbl = make_desc(b_lo + kk * 32);
+                                const uint64_t dal = a_lo_d + shift + (uint64_t)(kk * 2), dbl = b_lo_d + (uint64_t)(kk * 2);
                                 mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));
                                 mma_tf32(acc, dah, dbl, idesc, 1u);
                                 mma_tf32(acc, dah, dbh, idesc, 1u);
@@ -231,12 +232,13 @@ __global__ void __launch_bounds__(kPHaloThreads, 1) conv_halo_persist_kernel(con
                         }
                         mma_commit(b_empty(s));
                     }
-                    mma_commit(patch_empty(buf));
+                    __syncwarp();
                 }
-                mma_commit(tmem_full(abuf));
+                if (leader) mma_commit(patch_empty(buf));
             }
+            if (leader) mma_commit(tmem_full(abuf));
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == LOAD_WARP) {
         if (lane == 0) {
             constexpr uint32_t BYTES = Cfg::B_STAGE;

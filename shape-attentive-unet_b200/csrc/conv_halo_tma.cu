@@ -25,7 +25,10 @@ struct HaloTP {
     int tiles_x, tiles_y, nchunk;
     int ntile_n, ntiles;                          // tile id = spatial tile * ntile_n + n tile
     const float* wt;
+    long long* prof;                              // optional per-CTA cycle counters (tools/bench_conv.py, SAUNET_TC_PROF): [148][16]
 };
+#define TP_T0() long long pt0__ = p.prof ? clock64() : 0
+#define TP_ADD(var) do { if (p.prof) { long long t1__ = clock64(); (var) += t1__ - pt0__; pt0__ = t1__; } } while (0)
 
 constexpr int kTPitch = 10;                         // patch rows per image row: stride-byte-offset 1280 (verified: any multiple of 128 works)
 constexpr int kTPatchRows = 18 * kTPitch;
@@ -131,11 +134,15 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
             int f = 0;
+            long long w_pe = 0;
+            const long long kt0 = p.prof ? clock64() : 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 int b, y0, x0, n0; tile_coords(ti, b, y0, x0, n0);
                 for (int cc = 0; cc < nchunk; ++cc, ++f) {
                     const int buf = f % NBUF; const uint32_t ph = (f / NBUF) & 1;
+                    TP_T0();
                     mbar_wait(patch_empty(buf), ph ^ 1u);
+                    TP_ADD(w_pe);
                     mbar_expect_tx(raw_full(buf), kTBoxBytes);
                     // coordinates innermost first: channel, x, y, image; negative / past-the-end = zero fill
                     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
@@ -143,6 +150,7 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                                    "r"(y0 - 1), "r"(b), "r"(raw_full(buf)) : "memory");
                 }
             }
+            if (p.prof) { long long* o = p.prof + blockIdx.x * 16; o[0] = clock64() - kt0; o[1] = w_pe; }
         }
         __syncwarp();
     } else if (warp < NPW) {
@@ -163,6 +171,7 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
         }
         const bool pro = d.in_scale != nullptr;
         int f = 0;
+        long long x_wait = 0, x_work = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             unsigned inb = 0;             // items that are real pixels (the prologue must leave the zero padding alone)
             if (pro) {
@@ -184,7 +193,9 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                 }
                 uint8_t* hi_img = sgen + buf * Cfg::PATCH;
                 uint8_t* lo_img = hi_img + kTPatchBytes;
+                TP_T0();
                 mbar_wait(raw_full(buf), ph);
+                TP_ADD(x_wait);
                 if (pro || NPASS == 3 || Opnd<NPASS>::BF) {
                     float4 v[kTHaloIters];
 #pragma unroll
@@ -211,53 +222,69 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(patch_full(buf));
+                TP_ADD(x_work);
             }
         }
+        if (p.prof && tid == 0) { long long* o = p.prof + blockIdx.x * 16; o[2] = x_wait; o[3] = x_work; }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
-            using Op = Opnd<NPASS>;
-            const uint32_t idesc = Op::idesc(BN);
-            const uint32_t idesc2 = Op::idesc(2 * BN);
-            int f = 0, g = 0;                     // flat patch / weight-stage counters
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                const int abuf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
-                mbar_wait(tmem_empty(abuf), tph ^ 1u);
-                tc_fence_after();
-                int kb = 0;
-                for (int cc = 0; cc < nchunk; ++cc, ++f) {
-                    const int buf = f % NBUF; const uint32_t pph = (f / NBUF) & 1;
-                    mbar_wait(patch_full(buf), pph);
-                    const int krem = d.Cin - cc * 32;                                                 // zero-padded K tail: skip it
-                    const int ksteps = krem >= 32 ? Op::KSTEPS : (Op::BF ? (krem + 15) / 16 : (krem + 7) / 8);
-                    const uint32_t a_hi0 = sbase + buf * Cfg::PATCH;
-                    const uint32_t a_lo0 = a_hi0 + kTPatchBytes;
-                    for (int tg = 0; tg < 9 / Cfg::G; ++tg, ++g) {
-                        const int s = g % NSTB; const uint32_t ph = (g / NSTB) & 1;
-                        mbar_wait(b_full(s), ph);
-                        tc_fence_after();
+        // The whole warp runs the loop CONVERGED (all lanes poll the barriers, all lanes hold the same uniform state) and
+        // one elected lane issues the MMAs / commits.  With the loop inside `if (lane == 0)` the compiler wraps every
+        // tcgen05.mma in an ELECT / BRA.U.ANY loop and rebuilds both 64-bit descriptors from scratch -- ~17 dependent
+        // uniform-datapath instructions, 70 (tf32) to 170 (bf16) clocks per MMA on the one issuing thread, which the
+        // per-role counters showed to be THE bound of every narrow tile (mma:issue 76-97 % of the kernel).  Descriptors are
+        // now templates (address field 0) advanced by 32-bit adds: an operand address only moves the low 14 bits.
+        using Op = Opnd<NPASS>;
+        const uint32_t idesc = Op::idesc(BN);
+        const uint32_t idesc2 = Op::idesc(2 * BN);
+        const uint64_t a_tmpl = Op::desc(0, kTPitch * Op::ROW), b_tmpl = Op::desc(0);
+        const bool leader = elect_one();
+        int f = 0, g = 0;                     // flat patch / weight-stage counters
+        long long m_te = 0, m_pf = 0, m_bf = 0, m_is = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int abuf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
+            TP_T0();
+            mbar_wait(tmem_empty(abuf), tph ^ 1u);
+            TP_ADD(m_te);
+            tc_fence_after();
+            int kb = 0;
+            for (int cc = 0; cc < nchunk; ++cc, ++f) {
+                const int buf = f % NBUF; const uint32_t pph = (f / NBUF) & 1;
+                mbar_wait(patch_full(buf), pph);
+                TP_ADD(m_pf);
+                const int krem = d.Cin - cc * 32;                                                 // zero-padded K tail: skip it
+                const int ksteps = krem >= 32 ? Op::KSTEPS : (Op::BF ? (krem + 15) / 16 : (krem + 7) / 8);
+                const uint32_t a_hi0 = sbase + buf * Cfg::PATCH;
+                const uint64_t a_hi_d = a_tmpl + (uint64_t)(a_hi0 >> 4), a_lo_d = a_hi_d + (uint64_t)(kTPatchBytes >> 4);
+                for (int tg = 0; tg < 9 / Cfg::G; ++tg, ++g) {
+                    const int s = g % NSTB; const uint32_t ph = (g / NSTB) & 1;
+                    mbar_wait(b_full(s), ph);
+                    TP_ADD(m_bf);
+                    tc_fence_after();
+                    if (leader) {
+                        const uint64_t b_d0 = b_tmpl + (uint64_t)((b_base + s * Cfg::B_STAGE) >> 4);
 #pragma unroll
-                        for (int t = 0; t < Cfg::G; ++t, ++kb) {
+                        for (int t = 0; t < Cfg::G; ++t) {
                             const int tap = tg * Cfg::G + t;
                             const int ky = tap / 3, kx = tap - ky * 3;
-                            const uint32_t shift = (uint32_t)(ky * kTPitch + kx) * Op::ROW;
-                            const uint32_t b_hi = b_base + s * Cfg::B_STAGE + t * Cfg::B_TAP;
-                            const uint32_t b_lo = b_hi + BN * 128;
-                            const uint32_t acc = tmem + (uint32_t)(abuf * Cfg::BUF_COLS + (kb % NACC) * Cfg::ACC_COLS);
-                            const uint32_t fresh = (kb < NACC) ? 0u : 1u;
+                            const uint64_t shift = (uint64_t)(((ky * kTPitch + kx) * Op::ROW) >> 4);
+                            const uint64_t b_hi_d = b_d0 + (uint64_t)((t * Cfg::B_TAP) >> 4), b_lo_d = b_hi_d + (uint64_t)((BN * 128) >> 4);
+                            const int kbt = kb + t;
+                            const uint32_t acc = tmem + (uint32_t)(abuf * Cfg::BUF_COLS + (kbt % NACC) * Cfg::ACC_COLS);
+                            const uint32_t fresh = (kbt < NACC) ? 0u : 1u;
 #pragma unroll
                             for (int kk = 0; kk < 4; ++kk) {
                                 if (kk >= ksteps) break;
                                 if (Op::BF) {          // the operand is the bf16 image behind the raw patch
-                                    Op::mma(acc, Op::desc(a_lo0 + shift + kk * 32, kTPitch * Op::ROW), Op::desc(b_hi + kk * 32), idesc, (kk ? 1u : fresh));
+                                    Op::mma(acc, a_lo_d + shift + (uint64_t)(kk * 2), b_hi_d + (uint64_t)(kk * 2), idesc, (kk ? 1u : fresh));
                                     continue;
                                 }
-                                const uint64_t dah = make_desc_sbo(a_hi0 + shift + kk * 32, kTPitch * 128), dbh = make_desc(b_hi + kk * 32);
+                                const uint64_t dah = a_hi_d + shift + (uint64_t)(kk * 2), dbh = b_hi_d + (uint64_t)(kk * 2);
                                 if (Cfg::CAT) {
-                                    const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kTPitch * 128);
+                                    const uint64_t dal = a_lo_d + shift + (uint64_t)(kk * 2);
                                     mma_tf32(acc, dah, dbh, idesc2, (kk ? 1u : fresh));       // [hi*hi | hi*lo]: B rows BN..2BN-1 are the lo image
                                     mma_tf32(acc + BN, dal, dbh, idesc, 1u);                  // lo*hi joins the small-terms half
                                 } else if (NPASS == 3) {
-                                    const uint64_t dal = make_desc_sbo(a_lo0 + shift + kk * 32, kTPitch * 128), dbl = make_desc(b_lo + kk * 32);
+                                    const uint64_t dal = a_lo_d + shift + (uint64_t)(kk * 2), dbl = b_lo_d + (uint64_t)(kk * 2);
                                     mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));
                                     mma_tf32(acc, dah, dbl, idesc, 1u);
                                     mma_tf32(acc, dah, dbh, idesc, 1u);
@@ -268,27 +295,36 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                         }
                         mma_commit(b_empty(s));
                     }
-                    mma_commit(patch_empty(buf));
+                    kb += Cfg::G;
+                    __syncwarp();
+                    TP_ADD(m_is);
                 }
-                mma_commit(tmem_full(abuf));
+                if (leader) mma_commit(patch_empty(buf));
             }
+            if (leader) mma_commit(tmem_full(abuf));
+            __syncwarp();
         }
+        if (p.prof && leader) { long long* o = p.prof + blockIdx.x * 16; o[4] = m_te; o[5] = m_pf; o[6] = m_bf; o[7] = m_is; }
         __syncwarp();
     } else if (warp == LOAD_WARP) {
         if (lane == 0) {
             constexpr uint32_t BYTES = Cfg::B_STAGE;
             const int nkb = nchunk * 9 / Cfg::G;          // weight stages per tile (G consecutive taps each)
             int g = 0;
+            long long l_be = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int nt = ((int)blockIdx.x + ti * (int)gridDim.x) % p.ntile_n;
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wt) + (size_t)nt * nkb * BYTES;
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
                     const int s = g % NSTB; const uint32_t ph = (g / NSTB) & 1;
+                    TP_T0();
                     mbar_wait(b_empty(s), ph ^ 1u);
+                    TP_ADD(l_be);
                     mbar_expect_tx(b_full(s), BYTES);
                     bulk_g2s(b_base + s * Cfg::B_STAGE, src + (size_t)kb * BYTES, BYTES, b_full(s));
                 }
             }
+            if (p.prof) { long long* o = p.prof + blockIdx.x * 16; o[8] = l_be; }
         }
         __syncwarp();
     } else {
@@ -299,6 +335,7 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
         const bool vst = (d.Cout % 4 == 0) && (d.y_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(d.y) & 15u) == 0);
         const int nkb = nchunk * 9;
         const int nacc = nkb < NACC ? nkb : NACC;
+        long long e_wait = 0, e_work = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
             const int abuf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
             int b, y0, x0, n0; tile_coords(ti, b, y0, x0, n0);
@@ -307,7 +344,9 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
             float* yp = d.y + m * d.y_ld;
             const float rs = d.row_scale ? (d.row_scale[m] + d.row_scale_add) : 1.f;
             if (ti > 0 && d.stat_sum) asm volatile("bar.sync 1, 256;" ::: "memory");      // red[] of the previous tile consumed
+            TP_T0();
             mbar_wait(tmem_full(abuf), tph);
+            TP_ADD(e_wait);
             tc_fence_after();
             const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(abuf * Cfg::BUF_COLS);
             for (int c0 = half * 16; c0 < BN; c0 += 32) {
@@ -374,7 +413,9 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                     }
                 }
             }
+            TP_ADD(e_work);
         }
+        if (p.prof && etid == 0) { long long* o = p.prof + blockIdx.x * 16; o[9] = e_wait; o[10] = e_work; }
     }
     tc_fence_before();
     __syncthreads();
@@ -430,6 +471,11 @@ static int launch_halo_tma(const HaloTP& p0, cudaStream_t st) {
     if (rc != SAUNET_OK) return rc;
     p.ntile_n = cdiv(p.d.Cout, BN);
     p.ntiles = p.d.B * p.tiles_y * p.tiles_x * p.ntile_n;
+    static long long* const prof_ptr = []() -> long long* {          // debugging aid, read once per process
+        const char* pe = getenv("SAUNET_TC_PROF");
+        return pe ? reinterpret_cast<long long*>(strtoull(pe, nullptr, 0)) : nullptr;
+    }();
+    p.prof = prof_ptr;
     const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
     conv_halo_tma_kernel<BN, NPASS><<<grid, kTHaloThreads, Cfg::SMEM, st>>>(p, tm);
     SAUNET_CHECK_LAUNCH("conv_halo_tma_kernel");

@@ -134,10 +134,13 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
             if (f + 1 < total) { load_next(va, ta); store_item(f + 1, vb, tb); }
         }
     } else if (warp == MMA_WARP) {
-        if (lane == 0) {
+        // converged warp, one elected lane issues; descriptors = templates advanced by adds (see conv_halo_tma.cu)
+        {
             // D=f32, A=B=tf32 (bf16), both K-major, N=256 (pixels), M=128 (channels)
             using Op = Opnd<NPASS>;
             const uint32_t idesc = Op::idesc(kTNP);
+            const uint64_t tmpl = Op::desc(0);
+            const bool leader = elect_one();
             int f = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int buf = ti & 1; const uint32_t tph = (ti >> 1) & 1;
@@ -148,24 +151,28 @@ __global__ void __launch_bounds__(kTThreads, 1) conv_pw_t_kernel(const __grid_co
                     mbar_wait(full_x(s), ph);
                     mbar_wait(full_w(s), ph);
                     tc_fence_after();
-                    const uint32_t x_hi = sbase + s * Cfg::STAGE, x_lo = x_hi + Cfg::X_IMG;
-                    const uint32_t w_hi = x_hi + Cfg::NOP * Cfg::X_IMG, w_lo = w_hi + Cfg::W_IMG;
-                    const uint32_t acc = tmem + (uint32_t)(buf * kTNP);
+                    if (leader) {
+                        const uint64_t x_hi = tmpl + (uint64_t)((sbase + s * Cfg::STAGE) >> 4), x_lo = x_hi + (uint64_t)(Cfg::X_IMG >> 4);
+                        const uint64_t w_hi = x_hi + (uint64_t)((Cfg::NOP * Cfg::X_IMG) >> 4), w_lo = w_hi + (uint64_t)(Cfg::W_IMG >> 4);
+                        const uint32_t acc = tmem + (uint32_t)(buf * kTNP);
 #pragma unroll
-                    for (int kk = 0; kk < Op::KSTEPS; ++kk) {
-                        const uint64_t dwh = Op::desc(w_hi + kk * 32), dxh = Op::desc(x_hi + kk * 32);
-                        if (NPASS == 3) {
-                            const uint64_t dwl = Op::desc(w_lo + kk * 32), dxl = Op::desc(x_lo + kk * 32);
-                            mma_tf32(acc, dwl, dxh, idesc, (kb | kk) ? 1u : 0u);
-                            mma_tf32(acc, dwh, dxl, idesc, 1u);
-                            mma_tf32(acc, dwh, dxh, idesc, 1u);
-                        } else {
-                            Op::mma(acc, dwh, dxh, idesc, (kb | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < Op::KSTEPS; ++kk) {
+                            const uint64_t dwh = w_hi + (uint64_t)(kk * 2), dxh = x_hi + (uint64_t)(kk * 2);
+                            if (NPASS == 3) {
+                                const uint64_t dwl = w_lo + (uint64_t)(kk * 2), dxl = x_lo + (uint64_t)(kk * 2);
+                                mma_tf32(acc, dwl, dxh, idesc, (kb | kk) ? 1u : 0u);
+                                mma_tf32(acc, dwh, dxl, idesc, 1u);
+                                mma_tf32(acc, dwh, dxh, idesc, 1u);
+                            } else {
+                                Op::mma(acc, dwh, dxh, idesc, (kb | kk) ? 1u : 0u);
+                            }
                         }
+                        mma_commit(empty(s));
                     }
-                    mma_commit(empty(s));
+                    __syncwarp();
                 }
-                mma_commit(tmem_full(buf));
+                if (leader) mma_commit(tmem_full(buf));
+                __syncwarp();
             }
         }
         __syncwarp();

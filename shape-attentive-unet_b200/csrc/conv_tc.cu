@@ -224,10 +224,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         }
     } else if (warp == MMA_WARP) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // converged warp, one elected lane issues; descriptors = templates advanced by adds (see conv_halo_tma.cu: with the
+        // loop inside `if (lane == 0)` every tcgen05.mma cost the issuing thread 70-170 clocks)
+        {
             // instruction descriptor: D=f32, A=B=tf32 (bf16), both K-major, N=BN, M=128
             using Op = Opnd<NPASS>;
             const uint32_t idesc = Op::idesc(BN);
+            const uint64_t tmpl = Op::desc(0);
+            const bool leader = elect_one();
             long long mw_te = 0, mw_fa = 0, mw_fb = 0, mw_issue = 0;
             int f = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
@@ -243,30 +247,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     mbar_wait(full_b(s), ph);
                     TC_PROF_ADD(mw_fb);
                     tc_fence_after();
-                    const uint32_t a_hi = sbase + s * Cfg::STAGE;
-                    const uint32_t a_lo = a_hi + Cfg::A_BYTES;
-                    const uint32_t b_hi = a_hi + Cfg::NOP * Cfg::A_BYTES;
-                    const uint32_t b_lo = b_hi + Cfg::B_BYTES;
-                    const uint32_t acc = tmem + (uint32_t)(buf * Cfg::BUF_COLS + (kb % NACC) * Cfg::ACC_COLS);
-                    const uint32_t fresh = (kb < NACC) ? 0u : 1u;          // first k-block of each accumulator overwrites
+                    if (leader) {
+                        const uint64_t a_hi = tmpl + (uint64_t)((sbase + s * Cfg::STAGE) >> 4);
+                        const uint64_t a_lo = a_hi + (uint64_t)(Cfg::A_BYTES >> 4);
+                        const uint64_t b_hi = a_hi + (uint64_t)((Cfg::NOP * Cfg::A_BYTES) >> 4);
+                        const uint64_t b_lo = b_hi + (uint64_t)(Cfg::B_BYTES >> 4);
+                        const uint32_t acc = tmem + (uint32_t)(buf * Cfg::BUF_COLS + (kb % NACC) * Cfg::ACC_COLS);
+                        const uint32_t fresh = (kb < NACC) ? 0u : 1u;          // first k-block of each accumulator overwrites
 #pragma unroll
-                    for (int kk = 0; kk < Op::KSTEPS; ++kk) {
-                        const uint64_t dah = Op::desc(a_hi + kk * 32), dbh = Op::desc(b_hi + kk * 32);
-                        if (NPASS == 3) {
-                            const uint64_t dal = Op::desc(a_lo + kk * 32), dbl = Op::desc(b_lo + kk * 32);
-                            mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));       // small terms first
-                            mma_tf32(acc, dah, dbl, idesc, 1u);
-                            mma_tf32(acc, dah, dbh, idesc, 1u);
-                        } else {
-                            Op::mma(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                        for (int kk = 0; kk < Op::KSTEPS; ++kk) {
+                            const uint64_t dah = a_hi + (uint64_t)(kk * 2), dbh = b_hi + (uint64_t)(kk * 2);
+                            if (NPASS == 3) {
+                                const uint64_t dal = a_lo + (uint64_t)(kk * 2), dbl = b_lo + (uint64_t)(kk * 2);
+                                mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));       // small terms first
+                                mma_tf32(acc, dah, dbl, idesc, 1u);
+                                mma_tf32(acc, dah, dbh, idesc, 1u);
+                            } else {
+                                Op::mma(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                            }
                         }
+                        mma_commit(empty(s));
                     }
-                    mma_commit(empty(s));
+                    __syncwarp();
                     TC_PROF_ADD(mw_issue);
                 }
-                mma_commit(tmem_full(buf));
+                if (leader) mma_commit(tmem_full(buf));
+                __syncwarp();
             }
-            if (p.prof) {
+            if (p.prof && leader) {
                 long long* o = p.prof + blockIdx.x * 16;
                 o[4] = mw_te; o[5] = mw_fa; o[6] = mw_fb; o[7] = mw_issue;
             }

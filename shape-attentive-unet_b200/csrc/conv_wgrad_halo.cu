@@ -208,8 +208,9 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv_wgrad_halo_kernel(const __
         }
         tc_fence_before();
     } else {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: converged warp, one elected lane issues (see conv_halo_tma.cu) =================
+        const bool leader = elect_one();
+        {
             // D=f32, A=B=tf32, both MN-major, N=NT, M=128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(Cfg::NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv_wgrad_halo_kernel(const __
                 const uint32_t q_hi = sbase + s * Cfg::STAGE;
                 const uint64_t dqh0 = dQ | (uint64_t)(q_hi >> 4), dql0 = dQ | (uint64_t)((q_hi + Cfg::A_IMG) >> 4);
                 const uint32_t p_hi = q_hi + 2 * Cfg::A_IMG;
+                if (leader) {
 #pragma unroll 1
                 for (int acc = 0; acc < Cfg::NACC; ++acc) {
                     const int pl = acc / 3, ky = acc - pl * 3;
@@ -241,8 +243,10 @@ __global__ void __launch_bounds__(kWhThreads, 1) conv_wgrad_halo_kernel(const __
                     }
                 }
                 mma_commit(empty(s));
+                }
+                __syncwarp();
             }
-            mma_commit(accum_bar);
+            if (leader) mma_commit(accum_bar);
         }
         __syncwarp();
     }

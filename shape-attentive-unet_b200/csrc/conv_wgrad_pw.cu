@@ -177,8 +177,9 @@ __global__ void __launch_bounds__(kPwThreads, 1) conv_wgrad_pw_kernel(const __gr
         }
         tc_fence_before();
     } else {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer: converged warp, one elected lane issues (see conv_halo_tma.cu) =================
+        const bool leader = elect_one();
+        {
             const uint64_t dT = ((uint64_t)(kPwPlane >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
             const int ncol = (ncb + 15) & ~15;                       // N of the whole CTA, in MMAs of <= 256 columns
             for (int kb = 0; kb < nkb; ++kb) {
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(kPwThreads, 1) conv_wgrad_pw_kernel(const __gr
                 tc_fence_after();
                 const uint32_t a_hi = sbase + s * Cfg::STAGE;
                 const uint32_t b_hi = a_hi + 2 * Cfg::A_IMG;
+                if (leader) {
                 for (int n0 = 0; n0 < ncol; n0 += 256) {
                     const int n = (ncol - n0) < 256 ? (ncol - n0) : 256;
                     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
@@ -204,8 +206,10 @@ __global__ void __launch_bounds__(kPwThreads, 1) conv_wgrad_pw_kernel(const __gr
                     }
                 }
                 mma_commit(empty(s));
+                }
+                __syncwarp();
             }
-            mma_commit(accum_bar);
+            if (leader) mma_commit(accum_bar);
         }
         __syncwarp();
     }

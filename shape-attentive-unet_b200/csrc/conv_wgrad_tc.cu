@@ -242,8 +242,9 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
             tc_fence_before();
         }
     } else {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0 && nkb > 0) {
+        // ---------------- MMA issuer: converged warp, one elected lane issues (see conv_halo_tma.cu) ----------------
+        const bool leader = elect_one();
+        if (nkb > 0) {
             // D=f32, A=B=tf32, both MN-major (bits 15, 16), N=BN, M=128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -257,10 +258,14 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
                 const uint32_t s_lo = s_hi + Cfg::S_BYTES;
                 const uint32_t acc = tmem + (uint32_t)((kb % NACC) * BN);
                 const uint32_t fresh = (kb < NACC) ? 0u : 1u;
+                if (leader) {
+                const uint64_t tR = make_desc_mn(0, 512, 2048), tS = make_desc_mn(0, 512, BN * 16);      // templates: the address moves the low 14 bits only
+                const uint64_t drh0 = tR + (uint64_t)(r_hi >> 4), drl0 = tR + (uint64_t)(r_lo >> 4);
+                const uint64_t dsh0 = tS + (uint64_t)(s_hi >> 4), dsl0 = tS + (uint64_t)(s_lo >> 4);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {                 // 4 groups of 8 pixels
-                    const uint64_t drh = make_desc_mn(r_hi + j * 4096, 512, 2048), drl = make_desc_mn(r_lo + j * 4096, 512, 2048);
-                    const uint64_t dsh = make_desc_mn(s_hi + j * (BN * 32), 512, BN * 16), dsl = make_desc_mn(s_lo + j * (BN * 32), 512, BN * 16);
+                    const uint64_t drh = drh0 + (uint64_t)(j * 4096 >> 4), drl = drl0 + (uint64_t)(j * 4096 >> 4);
+                    const uint64_t dsh = dsh0 + (uint64_t)(j * (BN * 32) >> 4), dsl = dsl0 + (uint64_t)(j * (BN * 32) >> 4);
                     if (!one) {
                         mma_tf32(acc, drl, dsh, idesc, (j ? 1u : fresh));
                         mma_tf32(acc, drh, dsl, idesc, 1u);
@@ -268,8 +273,10 @@ __global__ void __launch_bounds__(kWgThreads, WgCfg<BN>::MIN_CTAS) conv_wgrad_tc
                     mma_tf32(acc, drh, dsh, idesc, one ? (j ? 1u : fresh) : 1u);
                 }
                 mma_commit(empty(s));
+                }
+                __syncwarp();
             }
-            mma_commit(accum_bar);
+            if (leader) mma_commit(accum_bar);
         }
         __syncwarp();
     }

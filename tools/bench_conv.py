@@ -20,6 +20,11 @@ w = torch.randn(Cout, Cin, k, k, device=dev) / (Cin * k * k) ** 0.5
 st = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
 dw = torch.zeros(k * k * Cin * Cout, device=dev)
 pro_state = torch.cat([0.5 + torch.rand(Cin), 0.3 * torch.randn(Cin)]).to(dev) if os.environ.get('PRO') else None
+prof = None
+if os.environ.get("PROF") and kind == "fwd":
+    # (the library reads SAUNET_TC_PROF once per process, at its first launch: set it before anything runs)
+    prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    os.environ["SAUNET_TC_PROF"] = str(prof.data_ptr())
 def run():
     if kind == "fwd":
         conv(tp, x, packed(tp, w, 0), Cout, k, k, y, H, W, offy=-(k // 2), offx=-(k // 2),
@@ -45,15 +50,17 @@ with torch.cuda.stream(side):
 ms = e0.elapsed_time(e1) / iters
 fl = 2.0 * B * H * W * k * k * Cin * Cout
 if os.environ.get("PROF") and kind == "fwd":
-    prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
-    os.environ["SAUNET_TC_PROF"] = str(prof.data_ptr())
+    prof.zero_()
     tp.stream = torch.cuda.current_stream().cuda_stream
     run(); torch.cuda.synchronize()
-    del os.environ["SAUNET_TC_PROF"]
     pr = prof.view(148, 16).double().cpu()
     pr = pr[pr[:, 0] > 0]
+    names_tma = ["total", "tma:wait_patch_empty", "xform:wait_raw_full", "xform:work", "mma:wait_tmem_empty", "mma:wait_patch_full",
+                 "mma:wait_b_full", "mma:issue+commit", "load:wait_b_empty", "epi:wait_tmem_full", "epi:work"]
     names = ["total", "prod:wait_empty", "prod:transform(+load latency)", "prod:fence+arrive", "mma:wait_tmem_empty", "mma:wait_full_a",
              "mma:wait_full_b", "mma:issue+commit", "epi:wait_tmem_full", "epi:work", "epi:tmem_ld", "epi:alu+st", "epi:fence+bar"]
+    if os.environ.get("PROF") == "tma":
+        names = names_tma
     tot = float(pr[:, 0].mean())
     print("  per-role cycles (mean over %d CTAs, kernel = %.0f cycles): " % (pr.shape[0], tot) +
           ", ".join("%s %.0f%%" % (n, 100 * float(pr[:, i].mean()) / tot) for i, n in enumerate(names) if i))
