@@ -54,7 +54,9 @@ struct HaloCfg {
     // the two halves accumulate in separate TMEM columns and are added in the epilogue.
     static constexpr bool CAT = (NPASS == 3) && (BN <= 64);
     static constexpr int ACC_COLS = (BN < 32 ? 32 : BN) * (CAT ? 2 : 1);
-    static constexpr int NACC = (256 / ACC_COLS) > 4 ? 4 : (256 / ACC_COLS);
+    // (bf16 operands: one accumulator -- the round-robin over several only serves the fp32-class error budget of 3xTF32, and
+    //  every extra accumulator is one more TMEM load per 16 columns in an epilogue that bounds the short-K tiles)
+    static constexpr int NACC = Op::BF ? 1 : ((256 / ACC_COLS) > 4 ? 4 : (256 / ACC_COLS));
     static constexpr int TMEM_COLS = NACC * ACC_COLS;
     static_assert(NSTB >= 2, "weight ring needs two stages");
 };

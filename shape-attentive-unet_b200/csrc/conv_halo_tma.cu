@@ -17,6 +17,7 @@
 // ring (cp.async.bulk), 18 patch TMA.
 #include "tc_common.cuh"
 #include <cuda.h>
+#include <type_traits>
 
 namespace saunet {
 
@@ -75,7 +76,9 @@ struct HaloTCfg {
     // the two halves accumulate in separate TMEM columns and are added in the epilogue.
     static constexpr bool CAT = (NPASS == 3) && (BN <= 64);
     static constexpr int ACC_COLS = (BN < 32 ? 32 : BN) * (CAT ? 2 : 1);
-    static constexpr int NACC = (256 / ACC_COLS) > 4 ? 4 : (256 / ACC_COLS);      // per accumulator buffer (2 buffers)
+    // (bf16 operands: one accumulator -- the round-robin over several only serves the fp32-class error budget of 3xTF32, and
+    //  every extra accumulator is one more TMEM load per 16 columns in an epilogue that bounds the short-K tiles)
+    static constexpr int NACC = Op::BF ? 1 : ((256 / ACC_COLS) > 4 ? 4 : (256 / ACC_COLS));
     static constexpr int BUF_COLS = NACC * ACC_COLS;
     static constexpr int TMEM_COLS = 2 * BUF_COLS <= 256 ? 256 : 512;
     static_assert(NSTB >= 2, "weight ring needs two stages");
@@ -262,37 +265,41 @@ __global__ void __launch_bounds__(kTHaloThreads, 1) conv_halo_tma_kernel(const _
                     tc_fence_after();
                     if (leader) {
                         const uint64_t b_d0 = b_tmpl + (uint64_t)((b_base + s * Cfg::B_STAGE) >> 4);
+                        // `nk`: K steps of this chunk -- a compile-time constant for whole chunks (fully unrolled, the MMAs of
+                        // a tap group issue back to back), a run-time count only for the zero-padded last chunk
+                        auto issue = [&](auto nk) {
 #pragma unroll
-                        for (int t = 0; t < Cfg::G; ++t) {
-                            const int tap = tg * Cfg::G + t;
-                            const int ky = tap / 3, kx = tap - ky * 3;
-                            const uint64_t shift = (uint64_t)(((ky * kTPitch + kx) * Op::ROW) >> 4);
-                            const uint64_t b_hi_d = b_d0 + (uint64_t)((t * Cfg::B_TAP) >> 4), b_lo_d = b_hi_d + (uint64_t)((BN * 128) >> 4);
-                            const int kbt = kb + t;
-                            const uint32_t acc = tmem + (uint32_t)(abuf * Cfg::BUF_COLS + (kbt % NACC) * Cfg::ACC_COLS);
-                            const uint32_t fresh = (kbt < NACC) ? 0u : 1u;
+                            for (int t = 0; t < Cfg::G; ++t) {
+                                const int tap = tg * Cfg::G + t;
+                                const int ky = tap / 3, kx = tap - ky * 3;
+                                const uint64_t shift = (uint64_t)(((ky * kTPitch + kx) * Op::ROW) >> 4);
+                                const uint64_t b_hi_d = b_d0 + (uint64_t)((t * Cfg::B_TAP) >> 4), b_lo_d = b_hi_d + (uint64_t)((BN * 128) >> 4);
+                                const int kbt = kb + t;
+                                const uint32_t acc = tmem + (uint32_t)(abuf * Cfg::BUF_COLS + (kbt % NACC) * Cfg::ACC_COLS);
+                                const uint32_t fresh = (kbt < NACC) ? 0u : 1u;
 #pragma unroll
-                            for (int kk = 0; kk < 4; ++kk) {
-                                if (kk >= ksteps) break;
-                                if (Op::BF) {          // the operand is the bf16 image behind the raw patch
-                                    Op::mma(acc, a_lo_d + shift + (uint64_t)(kk * 2), b_hi_d + (uint64_t)(kk * 2), idesc, (kk ? 1u : fresh));
-                                    continue;
-                                }
-                                const uint64_t dah = a_hi_d + shift + (uint64_t)(kk * 2), dbh = b_hi_d + (uint64_t)(kk * 2);
-                                if (Cfg::CAT) {
-                                    const uint64_t dal = a_lo_d + shift + (uint64_t)(kk * 2);
-                                    mma_tf32(acc, dah, dbh, idesc2, (kk ? 1u : fresh));       // [hi*hi | hi*lo]: B rows BN..2BN-1 are the lo image
-                                    mma_tf32(acc + BN, dal, dbh, idesc, 1u);                  // lo*hi joins the small-terms half
-                                } else if (NPASS == 3) {
-                                    const uint64_t dal = a_lo_d + shift + (uint64_t)(kk * 2), dbl = b_lo_d + (uint64_t)(kk * 2);
-                                    mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));
-                                    mma_tf32(acc, dah, dbl, idesc, 1u);
-                                    mma_tf32(acc, dah, dbh, idesc, 1u);
-                                } else {
-                                    mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                                for (int kk = 0; kk < nk; ++kk) {
+                                    if (Op::BF) {          // the operand is the bf16 image behind the raw patch
+                                        Op::mma(acc, a_lo_d + shift + (uint64_t)(kk * 2), b_hi_d + (uint64_t)(kk * 2), idesc, (kk ? 1u : fresh));
+                                        continue;
+                                    }
+                                    const uint64_t dah = a_hi_d + shift + (uint64_t)(kk * 2), dbh = b_hi_d + (uint64_t)(kk * 2);
+                                    if (Cfg::CAT) {
+                                        const uint64_t dal = a_lo_d + shift + (uint64_t)(kk * 2);
+                                        mma_tf32(acc, dah, dbh, idesc2, (kk ? 1u : fresh));       // [hi*hi | hi*lo]: B rows BN..2BN-1 are the lo image
+                                        mma_tf32(acc + BN, dal, dbh, idesc, 1u);                  // lo*hi joins the small-terms half
+                                    } else if (NPASS == 3) {
+                                        const uint64_t dal = a_lo_d + shift + (uint64_t)(kk * 2), dbl = b_lo_d + (uint64_t)(kk * 2);
+                                        mma_tf32(acc, dal, dbh, idesc, (kk ? 1u : fresh));
+                                        mma_tf32(acc, dah, dbl, idesc, 1u);
+                                        mma_tf32(acc, dah, dbh, idesc, 1u);
+                                    } else {
+                                        mma_tf32(acc, dah, dbh, idesc, (kk ? 1u : fresh));
+                                    }
                                 }
                             }
-                        }
+                        };
+                        if (krem >= 32) issue(std::integral_constant<int, Op::KSTEPS>{}); else issue(ksteps);
                         mma_commit(b_empty(s));
                     }
                     kb += Cfg::G;

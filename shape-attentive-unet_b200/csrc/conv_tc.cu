@@ -59,7 +59,9 @@ struct TcCfg {
     // The tensor core rounds its fp32 accumulator toward zero on every MMA, a bias that grows linearly with K
     // (measured 4.5e-9*K normalised).  Round-robin the k-blocks over NACC TMEM accumulators and add them in the
     // epilogue with round-to-nearest FADDs: the bias drops by ~NACC.
-    static constexpr int NACC = (512 / (NBUF * ACC_COLS)) > 4 ? 4 : (512 / (NBUF * ACC_COLS));
+    // (bf16 operands: one accumulator -- the round-robin over several only serves the fp32-class error budget of 3xTF32, and
+    //  every extra accumulator is one more TMEM load per 16 columns in an epilogue that bounds the short-K tiles)
+    static constexpr int NACC = Op::BF ? 1 : ((512 / (NBUF * ACC_COLS)) > 4 ? 4 : (512 / (NBUF * ACC_COLS)));
     static constexpr int BUF_COLS = NACC * ACC_COLS;
     static constexpr int TMEM_COLS = NBUF * BUF_COLS <= 256 ? 256 : 512;
 };
