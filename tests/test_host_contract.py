@@ -211,3 +211,42 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "config" in d and "workload" in d["config"] and d["dtype"] == "f32"
+
+
+def test_bf16_weight_image_sizes_and_precision_switch():
+    """Host-side contract of the bf16 operand class (BASELINE configs[2]): a bf16 tile image holds two elements per float of
+    storage (half the single-pass TF32 image, a quarter of the 3xTF32 one), for the plain and the chunk-major padded layout;
+    `engine.set_precision` accepts exactly the four documented classes and maps them onto (tile passes, wgrad precision)."""
+    from saunet_b200 import _C, engine
+    lib = _C.load()
+    for K, N, BN in ((288, 32, 32), (1152, 128, 128), (147, 64, 64)):
+        one, three, bf = (lib.saunet_tc_packed_floats(K, N, BN, p) for p in (1, 3, 16))
+        assert three == 2 * one and 2 * bf == one and bf > 0
+    for taps, Cin, N, BN in ((9, 16, 16, 16), (9, 48, 64, 64), (9, 128, 32, 32)):
+        one, three, bf = (lib.saunet_tc_packed_floats_cm(taps, Cin, N, BN, p) for p in (1, 3, 16))
+        assert three == 2 * one and 2 * bf == one and bf == ((Cin + 31) // 32) * taps * ((N + BN - 1) // BN) * BN * 16
+    prev = engine.get_precision()
+    try:
+        for name in ("fp32", "3xtf32", "tf32", "bf16"):
+            engine.set_precision(name)
+            assert engine.get_precision() == name
+        with pytest.raises(ValueError):
+            engine.set_precision("fp16")
+    finally:
+        engine.set_precision(prev)
+
+
+def test_bench_defaults_follow_dtype():
+    """`bench.py` with no flags runs BASELINE configs[1] (fp32 class, batch 16); `--dtype bf16` alone selects configs[2]'s
+    batch of 32 per GPU; the config text names the arithmetic class."""
+    import importlib
+    import sys as _sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in _sys.path:
+        _sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    c16 = bench.workload_config(16, 1, "train")
+    assert "batch 16/GPU" in c16["workload"] and "configs[1]" in c16["workload"] and "bf16" not in c16["workload"]
+    c32 = bench.workload_config(32, 8, "train_loop", dtype="bf16")
+    assert "configs[2]" in c32["workload"] and "bf16 tensor-core operands" in c32["workload"] and c32["global_batch"] == 256
+    assert c32["parallelism"] == "dp8"
