@@ -251,7 +251,7 @@ def run_ours(args):
         kern, (t_ms, cnt, fl, nb) = max(kagg.items(), key=lambda kv: kv[1][0])
         # DRAM traffic of one launch from the committed `ncu --set full` captures (profiles/r0?_*.md), next to
         # the algorithmic bytes of the captured geometry: traffic ~ algorithmic means no wasted re-reads
-        NCU = {"conv_halo_tma_kernel": ("profiles/r02_halo_tma_raw64.md", 487.6e6, "B16 256x256 64->64 3x3 (TMA-fed): 269.1 MB read + 218.4 MB written (part of the output still in L2) vs 537 MB algorithmic; 53.3 % tensor-pipe active"),
+        NCU = {"conv_halo_tma_kernel": ("profiles/r02_halo_tma_raw64_final.md", 487.9e6, "B16 256x256 64->64 3x3 (TMA-fed): 268.8 MB read + 219.1 MB written (part of the output still in L2) vs 537 MB algorithmic; 64.7 % tensor-pipe active"),
                "conv_pw_t_kernel": ("profiles/r02_pwt_bnbwd.md", 598.8e6, "B16 128x128 1x1 data gradient with the fused BatchNorm-backward epilogue: 470.1 MB read + 128.8 MB written"),
                "conv_wgrad_halo_kernel": ("profiles/r01_final_wgrad_halo.md", 176.2e6, "B16 128x128 128->32 3x3: 171.4 MB read + 4.8 MB written vs 168 MB algorithmic (Q 134 MB + dY 34 MB)"),
                "conv_halo_kernel": ("profiles/r01_final_halo_n32.md", 153.8e6, "B16 128x128 128->32 3x3: 134.6 MB read + 19.2 MB written vs 168 MB algorithmic"),
